@@ -1,0 +1,983 @@
+// api.cu — C ABI (include/frb200.h) over the sm_100a kernels: context, TMA descriptor
+// construction, the backbone layer program, gallery residency and the match pipeline.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/frb200.h"
+#include "gemm_sm100.cuh"
+#include "match_sm100.cuh"
+#include "simple_kernels.cuh"
+
+using namespace frb;
+
+static_assert(sizeof(frb_warp_job) == sizeof(WarpJob), "warp job ABI mismatch");
+
+namespace {
+
+struct Plan {  // per-batch-size launch plan of the backbone
+  int B = 0;
+  const void* d_in = nullptr;  // the descriptors bake in the batch size and the input pointer
+  std::vector<CUtensorMap> tmA, tmA2, tmB;
+  std::vector<GemmParams> gp;
+  std::vector<int> block_n, grid;
+};
+
+}  // namespace
+
+struct frb_ctx {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  std::mutex mu;
+  long long launches = 0;
+  PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+  PFN_cuTensorMapEncodeIm2col_v12000 encode_im2col = nullptr;
+  int driver_version = 0;
+
+  // constants
+  unsigned short* d_lut = nullptr;  // 256 bf16
+  short* d_wtab = nullptr;          // 32*32*4 int16
+
+  // backbone
+  std::vector<frb_layer_desc> layers;
+  uint8_t* d_blob = nullptr;
+  size_t blob_bytes = 0;
+  int n_bufs = 0;
+  std::vector<size_t> buf_elems_per_face;  // bf16 elements per face per buffer
+  std::vector<__nv_bfloat16*> d_bufs;
+  int bufs_capacity_B = 0;
+  float* d_fc_partial = nullptr;
+  size_t fc_partial_elems = 0;
+  float* d_emb2 = nullptr;  // flip fusion scratch [2B][512]
+  size_t emb2_elems = 0;
+  Plan plan;
+  double flops_per_face = 0.0;
+
+  // gallery
+  float* d_gal = nullptr;
+  __nv_bfloat16* d_gal_bf16 = nullptr;
+  long long gal_N = 0, gal_first = 0, gal_cap = 0;
+  float* d_gal_maxnorm = nullptr;
+  CUtensorMap tmG;
+
+  // match workspace
+  float* d_probe_f32 = nullptr;
+  __nv_bfloat16* d_probe_bf16 = nullptr;
+  float* d_cand_score = nullptr;
+  int* d_cand_idx = nullptr;
+  int* d_flagged = nullptr;
+  int* d_flag_rows = nullptr;
+  double* d_exact = nullptr;
+  size_t exact_elems = 0;
+  int match_cap_P = 0, match_cap_slices = 0;
+  std::vector<int> h_flagged;
+  int last_flagged = 0;
+  double* d_scores64_tmp = nullptr;
+  size_t scores64_tmp_elems = 0;
+
+  // host-API staging
+  uint8_t* d_stage_u8 = nullptr; size_t stage_u8_bytes = 0;
+  __nv_bfloat16* d_stage_in = nullptr; size_t stage_in_elems = 0;
+  float* d_stage_emb = nullptr; float* d_stage_norm = nullptr; size_t stage_emb_rows = 0;
+  float* d_stage_sc = nullptr; long long* d_stage_idx = nullptr; unsigned char* d_stage_acc = nullptr;
+  size_t stage_match_rows = 0; int stage_match_k = 0;
+  WarpJob* d_jobs = nullptr; int jobs_cap = 0;
+  cudaStream_t own_stream = nullptr;
+};
+
+namespace {
+
+int fail(frb_ctx* c, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return 1;
+}
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+template <typename T>
+int ensure(frb_ctx* ctx, T** p, size_t* cap, size_t need) {
+  if (*cap >= need && *p) return 0;
+  if (*p) CK(cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  CK(cudaMalloc(reinterpret_cast<void**>(p), need * sizeof(T)));
+  *cap = need;
+  return 0;
+}
+
+// CUTLASS applies the same fix-up for drivers <= 13.1 on tensors smaller than 128 KiB.
+void small_tensor_fixup(frb_ctx* ctx, CUtensorMap* m, size_t bytes) {
+  if (ctx->driver_version <= 13010 && bytes < 131072)
+    reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+}
+
+// 2D row-major bf16 tensor [rows][cols]; box = 64 cols x box_rows, 128B swizzle.
+int make_tmap_2d(frb_ctx* ctx, CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = ctx->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                                 es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ctx, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu box_rows=%u", (int)r,
+                (unsigned long long)cols, (unsigned long long)rows, box_rows);
+  small_tensor_fixup(ctx, m, cols * rows * 2);
+  return 0;
+}
+
+// NHWC bf16 activation [N][H][W][C] in im2col mode: 128 pixels x 64 channels per load.
+int make_tmap_im2col(frb_ctx* ctx, CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int ksize, int stride,
+                     int pad) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  // fprop corners (CUTLASS conv/collective/detail.hpp): lower = -pad, upper = pad - (ksize-1)*dilation
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = ctx->encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower,
+                                  upper, 64, 128, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ctx, "cuTensorMapEncodeIm2col failed (%d) N=%d H=%d W=%d C=%d k=%d s=%d p=%d", (int)r, N, H, W, C,
+                ksize, stride, pad);
+  small_tensor_fixup(ctx, m, (size_t)N * H * W * C * 2);
+  return 0;
+}
+
+template <int BN, int MODE>
+int launch_gemm_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& gp,
+                  int grid, cudaStream_t st) {
+  auto kern = gemm_sm100_kernel<BN, MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+    attr_set = true;
+  }
+  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(a, a2, b, gp);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int launch_gemm(frb_ctx* ctx, int block_n, int mode, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
+                const GemmParams& gp, int grid, cudaStream_t st) {
+  if (mode == A_IM2COL) {
+    if (block_n == 64) return launch_gemm_t<64, A_IM2COL>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 128) return launch_gemm_t<128, A_IM2COL>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 256) return launch_gemm_t<256, A_IM2COL>(ctx, a, a2, b, gp, grid, st);
+  } else {
+    if (block_n == 64) return launch_gemm_t<64, A_TILED>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 128) return launch_gemm_t<128, A_TILED>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 256) return launch_gemm_t<256, A_TILED>(ctx, a, a2, b, gp, grid, st);
+  }
+  return fail(ctx, "unsupported block_n %d", block_n);
+}
+
+int pick_block_n(int cout) { return cout >= 256 ? 256 : (cout >= 128 ? 128 : 64); }
+
+int out_dim(int in, int ksize, int stride, int pad) { return (in + 2 * pad - ksize) / stride + 1; }
+
+// Fill GemmParams + tensor maps for one CONV layer.
+int setup_conv(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, const void* d_sc, const void* d_res,
+               const void* d_w, const float* d_bias, const float* d_prelu, void* d_out, CUtensorMap* tmA,
+               CUtensorMap* tmA2, CUtensorMap* tmB, GemmParams* gp, int* block_n, int* grid) {
+  if (L.cin % 64 || L.cout % 64) return fail(ctx, "conv channels must be multiples of 64 (cin=%d cout=%d)", L.cin, L.cout);
+  if (!((L.ksize == 3 && L.pad == 1) || (L.ksize == 1 && L.pad == 0))) return fail(ctx, "unsupported conv geometry");
+  const int P = out_dim(L.hin, L.ksize, L.stride, L.pad), Q = out_dim(L.win, L.ksize, L.stride, L.pad);
+  memset(gp, 0, sizeof(*gp));
+  gp->M = B * P * Q;
+  gp->N = L.cout;
+  gp->cin_chunks = L.cin / 64;
+  gp->num_kb_main = L.ksize * L.ksize * gp->cin_chunks;
+  gp->num_kb_sc = (L.sc_buf >= 0 || d_sc) && L.sc_cin > 0 ? L.sc_cin / 64 : 0;
+  gp->num_splits = 1;
+  gp->P = P;
+  gp->Q = Q;
+  gp->stride = L.stride;
+  gp->pad = L.pad;
+  gp->sc_stride = L.sc_stride;
+  gp->sc_chunks = gp->num_kb_sc;
+  gp->bias = d_bias;
+  gp->bias_cases = L.bias_cases;
+  gp->prelu = L.has_prelu ? d_prelu : nullptr;
+  gp->residual = reinterpret_cast<const __nv_bfloat16*>(d_res);
+  gp->res_stride = L.res_stride;
+  gp->RH = L.res_h;
+  gp->RW = L.res_w;
+  gp->out = reinterpret_cast<__nv_bfloat16*>(d_out);
+  gp->out_f32 = nullptr;
+  if (make_tmap_im2col(ctx, tmA, d_in, B, L.hin, L.win, L.cin, L.ksize, L.stride, L.pad)) return 1;
+  if (gp->num_kb_sc > 0) {
+    if (out_dim(L.sc_hin, 1, L.sc_stride, 0) != P || out_dim(L.sc_win, 1, L.sc_stride, 0) != Q)
+      return fail(ctx, "shortcut conv output size mismatch");
+    if (make_tmap_im2col(ctx, tmA2, d_sc, B, L.sc_hin, L.sc_win, L.sc_cin, 1, L.sc_stride, 0)) return 1;
+  } else {
+    *tmA2 = *tmA;
+  }
+  const int ktot = (gp->num_kb_main + gp->num_kb_sc) * 64;
+  *block_n = pick_block_n(L.cout);
+  if (make_tmap_2d(ctx, tmB, d_w, ktot, L.cout, *block_n)) return 1;
+  const int tiles = ((gp->M + 127) / 128) * (L.cout / *block_n);
+  *grid = std::min(tiles, ctx->num_sms);
+  return 0;
+}
+
+int choose_splits(int num_kb, int want) {
+  want = std::max(1, std::min(want, num_kb));
+  const int per = (num_kb + want - 1) / want;
+  return (num_kb + per - 1) / per;
+}
+
+}  // namespace
+
+// ====================================================================== ctx
+extern "C" int frb_ctx_create(int device, frb_ctx** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  frb_ctx* ctx = new frb_ctx();
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "frb_ctx_create: cudaSetDevice(%d): %s\n", device, cudaGetErrorString(e));
+    delete ctx;
+    return 1;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess || prop.major != 10) {
+    fprintf(stderr, "frb_ctx_create: device %d is not sm_100 (cc %d.%d); this library has no fallback path\n", device,
+            prop.major, prop.minor);
+    delete ctx;
+    return 2;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  cudaDriverGetVersion(&ctx->driver_version);
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn) { fprintf(stderr, "frb: no cuTensorMapEncodeTiled\n"); delete ctx; return 3; }
+  ctx->encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn) { fprintf(stderr, "frb: no cuTensorMapEncodeIm2col\n"); delete ctx; return 3; }
+  ctx->encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+
+  // normalisation LUT: float32((x/255 - 0.5)/0.5) in f64 as numpy does (face_embedder.py:100), then bf16 RN
+  unsigned short lut[256];
+  for (int i = 0; i < 256; ++i) {
+    const float f = static_cast<float>((static_cast<double>(i) / 255.0 - 0.5) / 0.5);
+    const __nv_bfloat16 b = __float2bfloat16_rn(f);
+    memcpy(&lut[i], &b, 2);
+  }
+  // bilinear weight table as cv::initInterTab2D(INTER_LINEAR, fixpt=true) builds it
+  std::vector<short> wtab(32 * 32 * 4);
+  for (int ay = 0; ay < 32; ++ay)
+    for (int ax = 0; ax < 32; ++ax) {
+      const float fx = ax * (1.f / 32), fy = ay * (1.f / 32);
+      const float tx[2] = {1.f - fx, fx}, ty[2] = {1.f - fy, fy};
+      int iw[4], sum = 0;
+      for (int k1 = 0; k1 < 2; ++k1)
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const float v = ty[k1] * tx[k2];
+          int q = static_cast<int>(lrintf(v * 32768.f));
+          q = std::max(-32768, std::min(32767, q));
+          iw[k1 * 2 + k2] = q;
+          sum += q;
+        }
+      if (sum != 32768) {
+        const int diff = sum - 32768;
+        int kmax = 0, kmin = 0;  // first max / first min, scanning k1 then k2 within the central 2x2
+        for (int k = 1; k < 4; ++k) {
+          if (iw[k] > iw[kmax]) kmax = k;
+          if (iw[k] < iw[kmin]) kmin = k;
+        }
+        if (diff < 0) iw[kmax] -= diff; else iw[kmin] -= diff;
+      }
+      for (int k = 0; k < 4; ++k) wtab[(ay * 32 + ax) * 4 + k] = static_cast<short>(iw[k]);
+    }
+  if (cudaMalloc(&ctx->d_lut, sizeof(lut)) != cudaSuccess || cudaMalloc(&ctx->d_wtab, wtab.size() * 2) != cudaSuccess ||
+      cudaMemcpy(ctx->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(ctx->d_wtab, wtab.data(), wtab.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc(&ctx->d_gal_maxnorm, 4) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    fprintf(stderr, "frb_ctx_create: constant upload failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return 4;
+  }
+  *out = ctx;
+  return 0;
+}
+
+extern "C" void frb_ctx_destroy(frb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  void* ptrs[] = {ctx->d_lut, ctx->d_wtab, ctx->d_blob, ctx->d_fc_partial, ctx->d_emb2, ctx->d_gal, ctx->d_gal_bf16,
+                  ctx->d_gal_maxnorm, ctx->d_probe_f32, ctx->d_probe_bf16, ctx->d_cand_score, ctx->d_cand_idx,
+                  ctx->d_flagged, ctx->d_flag_rows, ctx->d_exact, ctx->d_scores64_tmp, ctx->d_stage_u8,
+                  ctx->d_stage_in, ctx->d_stage_emb, ctx->d_stage_norm, ctx->d_stage_sc, ctx->d_stage_idx,
+                  ctx->d_stage_acc, ctx->d_jobs};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (auto* b : ctx->d_bufs)
+    if (b) cudaFree(b);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" const char* frb_last_error(frb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+extern "C" long long frb_launch_count(frb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ====================================================================== preprocessing
+extern "C" int frb_preprocess_u8(frb_ctx* ctx, const void* d_in, int B, int S, void* d_out, int flip, void* stream) {
+  if (!ctx) return 1;
+  if (S != 112 && S != 224) return fail(ctx, "frb_preprocess_u8: S must be 112 or 224 (got %d)", S);
+  if (B <= 0) return 0;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  const size_t total = static_cast<size_t>(B) * 112 * 112;
+  preprocess_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint8_t*>(d_in), B, S, ctx->d_lut, reinterpret_cast<__nv_bfloat16*>(d_out), flip);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+extern "C" int frb_warp_normalize(frb_ctx* ctx, const void* d_src_base, const frb_warp_job* h_jobs, int B, int S,
+                                  void* d_out_u8, void* d_out_bf16, void* stream) {
+  if (!ctx) return 1;
+  if (B <= 0) return 0;
+  if (d_out_bf16 && S != 112) return fail(ctx, "frb_warp_normalize: bf16 output requires S == 112");
+  if (!d_out_u8 && !d_out_bf16) return fail(ctx, "frb_warp_normalize: no output requested");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ctx->jobs_cap < B) {
+    if (ctx->d_jobs) CK(cudaFree(ctx->d_jobs));
+    ctx->d_jobs = nullptr;
+    CK(cudaMalloc(&ctx->d_jobs, sizeof(WarpJob) * B));
+    ctx->jobs_cap = B;
+  }
+  CK(cudaMemcpyAsync(ctx->d_jobs, h_jobs, sizeof(WarpJob) * B, cudaMemcpyHostToDevice, st));
+  dim3 grid((S * S + 127) / 128, B);
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(d_src_base);
+  uint8_t* o8 = reinterpret_cast<uint8_t*>(d_out_u8);
+  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(d_out_bf16);
+  if (d_out_u8 && d_out_bf16)
+    warp_normalize_kernel<true, true><<<grid, 128, 0, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+  else if (d_out_u8)
+    warp_normalize_kernel<true, false><<<grid, 128, 0, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+  else
+    warp_normalize_kernel<false, true><<<grid, 128, 0, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+// ====================================================================== backbone
+extern "C" int frb_backbone_load(frb_ctx* ctx, const frb_layer_desc* layers, int n_layers, const void* h_blob,
+                                 size_t blob_bytes, int n_bufs) {
+  if (!ctx) return 1;
+  if (!layers || n_layers <= 0 || !h_blob || n_bufs <= 0) return fail(ctx, "frb_backbone_load: bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  ctx->layers.assign(layers, layers + n_layers);
+  if (ctx->d_blob) CK(cudaFree(ctx->d_blob));
+  ctx->d_blob = nullptr;
+  CK(cudaMalloc(&ctx->d_blob, blob_bytes));
+  CK(cudaMemcpy(ctx->d_blob, h_blob, blob_bytes, cudaMemcpyHostToDevice));
+  ctx->blob_bytes = blob_bytes;
+  for (auto* b : ctx->d_bufs)
+    if (b) CK(cudaFree(b));
+  ctx->d_bufs.assign(n_bufs, nullptr);
+  ctx->bufs_capacity_B = 0;
+  ctx->n_bufs = n_bufs;
+  ctx->buf_elems_per_face.assign(n_bufs, 0);
+  ctx->plan = Plan();
+  double flops = 0.0;
+  for (const auto& L : ctx->layers) {
+    if (L.w_off < 0 || static_cast<size_t>(L.w_off + L.w_bytes) > blob_bytes) return fail(ctx, "layer weights outside blob");
+    if (L.out_buf < 0 || L.out_buf >= n_bufs) return fail(ctx, "bad out_buf");
+    const int P = out_dim(L.hin, L.ksize, L.stride, L.pad), Q = out_dim(L.win, L.ksize, L.stride, L.pad);
+    size_t out_elems;
+    if (L.op == FRB_OP_FC) {
+      out_elems = 0;  // FC writes fp32 partials, not an activation buffer
+      flops += 2.0 * L.cin * L.cout;
+    } else {
+      out_elems = static_cast<size_t>(P) * Q * L.cout;
+      flops += 2.0 * P * Q * L.cout * (static_cast<double>(L.ksize) * L.ksize * L.cin + (L.sc_buf >= 0 ? L.sc_cin : 0));
+    }
+    ctx->buf_elems_per_face[L.out_buf] = std::max(ctx->buf_elems_per_face[L.out_buf], out_elems);
+  }
+  ctx->flops_per_face = flops;
+  return 0;
+}
+
+extern "C" double frb_backbone_flops_per_face(frb_ctx* ctx) { return ctx ? ctx->flops_per_face : 0.0; }
+
+namespace {
+
+int build_plan(frb_ctx* ctx, int B, const void* d_in) {
+  // (re)allocate activation buffers
+  if (ctx->bufs_capacity_B < B) {
+    for (int i = 0; i < ctx->n_bufs; ++i) {
+      if (ctx->d_bufs[i]) CK(cudaFree(ctx->d_bufs[i]));
+      ctx->d_bufs[i] = nullptr;
+      const size_t elems = std::max<size_t>(ctx->buf_elems_per_face[i], 64) * B;
+      CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_bufs[i]), elems * 2));
+    }
+    ctx->bufs_capacity_B = B;
+  }
+  const size_t nl = ctx->layers.size();
+  Plan& pl = ctx->plan;
+  pl.B = B;
+  pl.tmA.resize(nl); pl.tmA2.resize(nl); pl.tmB.resize(nl); pl.gp.resize(nl); pl.block_n.assign(nl, 0); pl.grid.assign(nl, 0);
+  for (size_t i = 0; i < nl; ++i) {
+    const frb_layer_desc& L = ctx->layers[i];
+    const void* in = L.in_buf < 0 ? d_in : ctx->d_bufs[L.in_buf];
+    const uint8_t* blob = ctx->d_blob;
+    if (L.op == FRB_OP_CONV) {
+      const void* sc = L.sc_buf >= 0 ? ctx->d_bufs[L.sc_buf] : nullptr;
+      const void* res = L.res_buf >= 0 ? ctx->d_bufs[L.res_buf] : nullptr;
+      if (setup_conv(ctx, L, B, in, sc, res, blob + L.w_off, reinterpret_cast<const float*>(blob + L.bias_off),
+                     reinterpret_cast<const float*>(blob + L.prelu_off), ctx->d_bufs[L.out_buf], &pl.tmA[i],
+                     &pl.tmA2[i], &pl.tmB[i], &pl.gp[i], &pl.block_n[i], &pl.grid[i]))
+        return 1;
+    } else if (L.op == FRB_OP_FC) {
+      if (L.cin % 64 || L.cout % 256) return fail(ctx, "FC dims unsupported (%d -> %d)", L.cin, L.cout);
+      GemmParams& gp = pl.gp[i];
+      memset(&gp, 0, sizeof(gp));
+      gp.M = B;
+      gp.N = L.cout;
+      gp.num_kb_main = L.cin / 64;
+      gp.num_kb_sc = 0;
+      const int mn_tiles = ((B + 127) / 128) * (L.cout / 256);
+      gp.num_splits = choose_splits(gp.num_kb_main, std::max(1, ctx->num_sms / mn_tiles));
+      const size_t need = static_cast<size_t>(gp.num_splits) * B * L.cout;
+      if (ctx->fc_partial_elems < need) {
+        if (ctx->d_fc_partial) CK(cudaFree(ctx->d_fc_partial));
+        ctx->d_fc_partial = nullptr;
+        CK(cudaMalloc(&ctx->d_fc_partial, need * 4));
+        ctx->fc_partial_elems = need;
+      }
+      gp.out_f32 = ctx->d_fc_partial;
+      if (make_tmap_2d(ctx, &pl.tmA[i], in, L.cin, B, 128)) return 1;
+      pl.tmA2[i] = pl.tmA[i];
+      if (make_tmap_2d(ctx, &pl.tmB[i], blob + L.w_off, L.cin, L.cout, 256)) return 1;
+      pl.block_n[i] = 256;
+      pl.grid[i] = std::min(mn_tiles * gp.num_splits, ctx->num_sms);
+    }
+  }
+  return 0;
+}
+
+int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, float* d_norm, void* d_emb_bf16,
+                 cudaStream_t st) {
+  if (ctx->layers.empty()) return fail(ctx, "frb_embed: no backbone loaded");
+  const int Bn = (flags & FRB_EMBED_FLIP) ? 2 * B : B;  // faces through the network
+  if (ctx->plan.B != Bn || ctx->plan.d_in != d_in || ctx->plan.gp.empty()) {
+    ctx->plan.gp.clear();
+    if (build_plan(ctx, Bn, d_in)) return 1;
+    ctx->plan.d_in = d_in;
+  }
+  Plan& pl = ctx->plan;
+  for (size_t i = 0; i < ctx->layers.size(); ++i) {
+    const frb_layer_desc& L = ctx->layers[i];
+    const uint8_t* blob = ctx->d_blob;
+    if (L.op == FRB_OP_STEM) {
+      const void* in = L.in_buf < 0 ? d_in : ctx->d_bufs[L.in_buf];
+      dim3 grid((L.win + 15) / 16, (L.hin + 15) / 16, Bn);
+      stem_conv_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                             reinterpret_cast<const float*>(blob + L.w_off),
+                                             reinterpret_cast<const float*>(blob + L.bias_off),
+                                             reinterpret_cast<const float*>(blob + L.prelu_off),
+                                             ctx->d_bufs[L.out_buf], L.hin, L.win);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    } else if (L.op == FRB_OP_CONV) {
+      if (launch_gemm(ctx, pl.block_n[i], A_IM2COL, pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
+    } else if (L.op == FRB_OP_FC) {
+      if (launch_gemm(ctx, 256, A_TILED, pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
+      const bool flipf = (flags & FRB_EMBED_FLIP) != 0;
+      float* emb_dst = d_emb;
+      void* bf_dst = d_emb_bf16;
+      if (flipf) {
+        const size_t need = static_cast<size_t>(Bn) * 512;
+        if (ctx->emb2_elems < need) {
+          if (ctx->d_emb2) CK(cudaFree(ctx->d_emb2));
+          ctx->d_emb2 = nullptr;
+          CK(cudaMalloc(&ctx->d_emb2, need * 4));
+          ctx->emb2_elems = need;
+        }
+        emb_dst = ctx->d_emb2;
+        bf_dst = nullptr;
+      }
+      // with flip fusion each half is normalised the way extract_embeddings_batch(normalize=True) does
+      const int renorm = (flags & FRB_EMBED_RENORM) || flipf ? 1 : 0;
+      fc_finalize_kernel<<<Bn, 128, 0, st>>>(ctx->d_fc_partial, pl.gp[i].num_splits, Bn,
+                                             reinterpret_cast<const float*>(blob + L.bias_off),
+                                             (flags & FRB_EMBED_L2) ? 1 : 0, renorm, emb_dst, flipf ? nullptr : d_norm,
+                                             reinterpret_cast<__nv_bfloat16*>(bf_dst));
+      CK(cudaGetLastError());
+      ctx->launches++;
+      if (flipf) {
+        flip_fuse_kernel<<<B, 128, 0, st>>>(ctx->d_emb2, B, d_emb, reinterpret_cast<__nv_bfloat16*>(d_emb_bf16));
+        CK(cudaGetLastError());
+        ctx->launches++;
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int frb_embed(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, float* d_norm,
+                         void* d_emb_bf16, void* stream) {
+  if (!ctx) return 1;
+  if (B <= 0) return 0;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  return embed_locked(ctx, d_in, B, flags, d_emb, d_norm, d_emb_bf16, static_cast<cudaStream_t>(stream));
+}
+
+// ====================================================================== gallery + match
+extern "C" int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, long long first_global_id, int is_device) {
+  if (!ctx) return 1;
+  if (N < 0) return fail(ctx, "frb_gallery_upload: negative N");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  if (N > ctx->gal_cap) {
+    if (ctx->d_gal) CK(cudaFree(ctx->d_gal));
+    if (ctx->d_gal_bf16) CK(cudaFree(ctx->d_gal_bf16));
+    ctx->d_gal = nullptr;
+    ctx->d_gal_bf16 = nullptr;
+    const long long cap = std::max<long long>(N, 256);
+    CK(cudaMalloc(&ctx->d_gal, static_cast<size_t>(cap) * 512 * 4));
+    CK(cudaMalloc(&ctx->d_gal_bf16, static_cast<size_t>(cap) * 512 * 2));
+    ctx->gal_cap = cap;
+  }
+  ctx->gal_N = N;
+  ctx->gal_first = first_global_id;
+  CK(cudaMemset(ctx->d_gal_maxnorm, 0, 4));
+  if (N == 0) return 0;
+  CK(cudaMemcpy(ctx->d_gal, g, static_cast<size_t>(N) * 512 * 4, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  gallery_prepare_kernel<<<static_cast<unsigned>((N + 7) / 8), 256>>>(ctx->d_gal, N, ctx->d_gal_bf16, ctx->d_gal_maxnorm);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaDeviceSynchronize());
+  if (make_tmap_2d(ctx, &ctx->tmG, ctx->d_gal_bf16, 512, static_cast<uint64_t>(N), kMatchBN)) return 1;
+  return 0;
+}
+
+extern "C" long long frb_gallery_size(frb_ctx* ctx) { return ctx ? ctx->gal_N : 0; }
+extern "C" int frb_match_last_flagged(frb_ctx* ctx) { return ctx ? ctx->last_flagged : 0; }
+
+namespace {
+
+constexpr long long kExactOnlyBelow = 4096;  // tiny galleries: the exact scan IS the match
+constexpr int kExactChunk = 16;              // probes per exact-scan pass
+
+int run_exact(frb_ctx* ctx, const float* d_probes_norm, const int* d_rows, int F, int k, float thr, float* d_scores,
+              long long* d_idx, unsigned char* d_accept, double* d_scores64, cudaStream_t st) {
+  const long long N = ctx->gal_N;
+  for (int f0 = 0; f0 < F; f0 += kExactChunk) {
+    const int fc = std::min(kExactChunk, F - f0);
+    const size_t need = static_cast<size_t>(fc) * N;
+    if (ctx->exact_elems < need) {
+      if (ctx->d_exact) CK(cudaFree(ctx->d_exact));
+      ctx->d_exact = nullptr;
+      CK(cudaMalloc(&ctx->d_exact, std::max<size_t>(need, 1) * 8));
+      ctx->exact_elems = need;
+    }
+    // rows == nullptr means probes f0..f0+fc-1 in order
+    const float* probes = d_rows ? d_probes_norm : d_probes_norm + static_cast<size_t>(f0) * 512;
+    const int* rows = d_rows ? d_rows + f0 : nullptr;
+    dim3 grid(static_cast<unsigned>(std::min<long long>((N + 7) / 8, 148 * 8)), fc);
+    match_exact_scores_kernel<<<grid, 256, 0, st>>>(ctx->d_gal, N, probes, rows, ctx->d_exact);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    const size_t oo = d_rows ? 0 : static_cast<size_t>(f0);
+    match_exact_topk_kernel<<<fc, 256, 0, st>>>(ctx->d_exact, N, rows, k, thr, ctx->gal_first, d_scores64 + oo * k,
+                                                d_idx + oo * k, d_scores + oo * k, d_accept + oo);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  return 0;
+}
+
+int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, int normalize, float* d_scores,
+                 long long* d_idx, unsigned char* d_accept, double* d_scores64, cudaStream_t st) {
+  if (k <= 0 || k > kRescore / 2) return fail(ctx, "frb_match: k must be in [1, %d]", kRescore / 2);
+  const long long N = ctx->gal_N;
+  // workspace
+  if (ctx->match_cap_P < P) {
+    if (ctx->d_probe_f32) CK(cudaFree(ctx->d_probe_f32));
+    if (ctx->d_probe_bf16) CK(cudaFree(ctx->d_probe_bf16));
+    if (ctx->d_flagged) CK(cudaFree(ctx->d_flagged));
+    if (ctx->d_flag_rows) CK(cudaFree(ctx->d_flag_rows));
+    if (ctx->d_cand_score) CK(cudaFree(ctx->d_cand_score));
+    if (ctx->d_cand_idx) CK(cudaFree(ctx->d_cand_idx));
+    ctx->d_probe_f32 = nullptr; ctx->d_probe_bf16 = nullptr; ctx->d_flagged = nullptr; ctx->d_flag_rows = nullptr;
+    ctx->d_cand_score = nullptr; ctx->d_cand_idx = nullptr; ctx->match_cap_slices = 0;
+    const int cap = std::max(P, 128);
+    CK(cudaMalloc(&ctx->d_probe_f32, static_cast<size_t>(cap) * 512 * 4));
+    CK(cudaMalloc(&ctx->d_probe_bf16, static_cast<size_t>(cap) * 512 * 2));
+    CK(cudaMalloc(&ctx->d_flagged, static_cast<size_t>(cap) * 4));
+    CK(cudaMalloc(&ctx->d_flag_rows, static_cast<size_t>(cap) * 4));
+    ctx->match_cap_P = cap;
+  }
+  double* s64 = d_scores64;
+  if (!s64) {
+    const size_t need = static_cast<size_t>(P) * k;
+    if (ctx->scores64_tmp_elems < need) {
+      if (ctx->d_scores64_tmp) CK(cudaFree(ctx->d_scores64_tmp));
+      ctx->d_scores64_tmp = nullptr;
+      CK(cudaMalloc(&ctx->d_scores64_tmp, need * 8));
+      ctx->scores64_tmp_elems = need;
+    }
+    s64 = ctx->d_scores64_tmp;
+  }
+  probe_prepare_kernel<<<P, 128, 0, st>>>(d_probes, normalize, ctx->d_probe_f32, ctx->d_probe_bf16);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  ctx->last_flagged = 0;
+  if (N < kExactOnlyBelow) {
+    if (N == 0) {
+      CK(cudaMemsetAsync(d_idx, 0xFF, static_cast<size_t>(P) * k * 8, st));
+      CK(cudaMemsetAsync(d_accept, 0, P, st));
+      // -inf scores
+      std::vector<float> ninf(static_cast<size_t>(P) * k, -INFINITY);
+      CK(cudaMemcpyAsync(d_scores, ninf.data(), ninf.size() * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      return 0;
+    }
+    return run_exact(ctx, ctx->d_probe_f32, nullptr, P, k, thr, d_scores, d_idx, d_accept, s64, st);
+  }
+  // ---- bf16 tensor-core filter ----
+  MatchParams mp;
+  mp.P = P;
+  mp.N = N;
+  mp.p_tiles = (P + 127) / 128;
+  mp.g_tiles = static_cast<int>((N + kMatchBN - 1) / kMatchBN);
+  int want_slices = std::max(1, (ctx->num_sms * 8 + mp.p_tiles - 1) / mp.p_tiles);
+  want_slices = std::min(want_slices, std::min(mp.g_tiles, kMaxCandPad / kCand));
+  mp.tiles_per_slice = (mp.g_tiles + want_slices - 1) / want_slices;
+  mp.slices = (mp.g_tiles + mp.tiles_per_slice - 1) / mp.tiles_per_slice;
+  if (ctx->match_cap_slices < mp.slices || !ctx->d_cand_score) {
+    if (ctx->d_cand_score) CK(cudaFree(ctx->d_cand_score));
+    if (ctx->d_cand_idx) CK(cudaFree(ctx->d_cand_idx));
+    ctx->d_cand_score = nullptr; ctx->d_cand_idx = nullptr;
+    const size_t n = static_cast<size_t>(ctx->match_cap_P) * mp.slices * kCand;
+    CK(cudaMalloc(&ctx->d_cand_score, n * 4));
+    CK(cudaMalloc(&ctx->d_cand_idx, n * 4));
+    ctx->match_cap_slices = mp.slices;
+  }
+  mp.cand_score = ctx->d_cand_score;
+  mp.cand_idx = ctx->d_cand_idx;
+  CUtensorMap tmP;
+  if (make_tmap_2d(ctx, &tmP, ctx->d_probe_bf16, 512, static_cast<uint64_t>(P), 128)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(match_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MatchSmem::kTotal));
+    attr_set = true;
+  }
+  const int grid = std::min(mp.p_tiles * mp.slices, ctx->num_sms);
+  match_filter_kernel<<<grid, kMatchThreads, MatchSmem::kTotal, st>>>(tmP, ctx->tmG, mp);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  FinalizeParams fp;
+  fp.cand_score = ctx->d_cand_score; fp.cand_idx = ctx->d_cand_idx; fp.slices = mp.slices;
+  fp.probes = ctx->d_probe_f32; fp.gallery = ctx->d_gal; fp.N = N; fp.first_global_id = ctx->gal_first;
+  fp.k = k; fp.thr = thr; fp.max_norm = ctx->d_gal_maxnorm;
+  fp.out_score = s64; fp.out_idx = d_idx; fp.out_score_f32 = d_scores; fp.out_accept = d_accept;
+  fp.flagged = ctx->d_flagged;
+  match_finalize_kernel<<<P, 128, 0, st>>>(fp);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  // rows whose proof failed get the exact scan (rare; needs one small D2H of the flags)
+  ctx->h_flagged.resize(P);
+  CK(cudaMemcpyAsync(ctx->h_flagged.data(), ctx->d_flagged, static_cast<size_t>(P) * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<int> rows;
+  for (int i = 0; i < P; ++i)
+    if (ctx->h_flagged[i]) rows.push_back(i);
+  ctx->last_flagged = static_cast<int>(rows.size());
+  if (!rows.empty()) {
+    CK(cudaMemcpyAsync(ctx->d_flag_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, st));
+    if (run_exact(ctx, ctx->d_probe_f32, ctx->d_flag_rows, static_cast<int>(rows.size()), k, thr, d_scores, d_idx,
+                  d_accept, s64, st))
+      return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int frb_match(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, int normalize, float* d_scores,
+                         long long* d_idx, unsigned char* d_accept, double* d_scores64, void* stream) {
+  if (!ctx) return 1;
+  if (P <= 0) return 0;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  return match_locked(ctx, d_probes, P, k, thr, normalize, d_scores, d_idx, d_accept, d_scores64,
+                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int frb_topk_merge(frb_ctx* ctx, const double* d_in_scores64, const long long* d_in_idx, int G, int P, int k,
+                              float thr, float* d_scores, long long* d_idx, unsigned char* d_accept,
+                              double* d_scores64, void* stream) {
+  if (!ctx) return 1;
+  if (P <= 0) return 0;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  double* s64 = d_scores64;
+  if (!s64) {
+    const size_t need = static_cast<size_t>(P) * k;
+    if (ctx->scores64_tmp_elems < need) {
+      if (ctx->d_scores64_tmp) CK(cudaFree(ctx->d_scores64_tmp));
+      ctx->d_scores64_tmp = nullptr;
+      CK(cudaMalloc(&ctx->d_scores64_tmp, need * 8));
+      ctx->scores64_tmp_elems = need;
+    }
+    s64 = ctx->d_scores64_tmp;
+  }
+  topk_merge_kernel<<<(P + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_in_scores64, d_in_idx, G, P, k, thr,
+                                                                                 s64, d_idx, d_scores, d_accept);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+// ====================================================================== host-buffer entry points
+namespace {
+
+int stage_embed(frb_ctx* ctx, int B, int flags) {
+  const int Bn = (flags & FRB_EMBED_FLIP) ? 2 * B : B;
+  if (ensure(ctx, &ctx->d_stage_in, &ctx->stage_in_elems, static_cast<size_t>(Bn) * 112 * 112 * 3)) return 1;
+  if (ctx->stage_emb_rows < static_cast<size_t>(B)) {
+    if (ctx->d_stage_emb) CK(cudaFree(ctx->d_stage_emb));
+    if (ctx->d_stage_norm) CK(cudaFree(ctx->d_stage_norm));
+    ctx->d_stage_emb = nullptr; ctx->d_stage_norm = nullptr;
+    CK(cudaMalloc(&ctx->d_stage_emb, static_cast<size_t>(B) * 512 * 4));
+    CK(cudaMalloc(&ctx->d_stage_norm, static_cast<size_t>(B) * 4));
+    ctx->stage_emb_rows = B;
+  }
+  return 0;
+}
+
+int stage_match(frb_ctx* ctx, int P, int k) {
+  if (ctx->stage_match_rows < static_cast<size_t>(P) || ctx->stage_match_k < k) {
+    if (ctx->d_stage_sc) CK(cudaFree(ctx->d_stage_sc));
+    if (ctx->d_stage_idx) CK(cudaFree(ctx->d_stage_idx));
+    if (ctx->d_stage_acc) CK(cudaFree(ctx->d_stage_acc));
+    ctx->d_stage_sc = nullptr; ctx->d_stage_idx = nullptr; ctx->d_stage_acc = nullptr;
+    const size_t rows = std::max<size_t>(P, ctx->stage_match_rows);
+    const int kk = std::max(k, ctx->stage_match_k);
+    CK(cudaMalloc(&ctx->d_stage_sc, rows * kk * 4));
+    CK(cudaMalloc(&ctx->d_stage_idx, rows * kk * 8));
+    CK(cudaMalloc(&ctx->d_stage_acc, rows));
+    ctx->stage_match_rows = rows;
+    ctx->stage_match_k = kk;
+  }
+  return 0;
+}
+
+int embed_host_locked(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S, int flags, cudaStream_t st) {
+  if (S != 112 && S != 224) return fail(ctx, "S must be 112 or 224 (got %d)", S);
+  const size_t in_bytes = static_cast<size_t>(B) * S * S * 3;
+  if (ensure(ctx, &ctx->d_stage_u8, &ctx->stage_u8_bytes, in_bytes)) return 1;
+  if (stage_embed(ctx, B, flags)) return 1;
+  CK(cudaMemcpyAsync(ctx->d_stage_u8, h_rgb, in_bytes, cudaMemcpyHostToDevice, st));
+  const size_t total = static_cast<size_t>(B) * 112 * 112;
+  preprocess_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      ctx->d_stage_u8, B, S, ctx->d_lut, ctx->d_stage_in, (flags & FRB_EMBED_FLIP) ? 1 : 0);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return embed_locked(ctx, ctx->d_stage_in, B, flags, ctx->d_stage_emb, ctx->d_stage_norm, nullptr, st);
+}
+
+}  // namespace
+
+extern "C" int frb_embed_host(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S, int flags, float* h_emb, float* h_norm) {
+  if (!ctx) return 1;
+  if (B <= 0) return 0;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->own_stream;
+  if (embed_host_locked(ctx, h_rgb, B, S, flags, st)) return 1;
+  CK(cudaMemcpyAsync(h_emb, ctx->d_stage_emb, static_cast<size_t>(B) * 512 * 4, cudaMemcpyDeviceToHost, st));
+  if (h_norm) CK(cudaMemcpyAsync(h_norm, ctx->d_stage_norm, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int frb_match_host(frb_ctx* ctx, const float* h_probes, int P, int k, float thr, int normalize,
+                              float* h_scores, long long* h_idx, unsigned char* h_accept) {
+  if (!ctx) return 1;
+  if (P <= 0) return 0;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->own_stream;
+  if (stage_match(ctx, P, k)) return 1;
+  if (ctx->stage_emb_rows < static_cast<size_t>(P)) {
+    if (ctx->d_stage_emb) CK(cudaFree(ctx->d_stage_emb));
+    if (ctx->d_stage_norm) CK(cudaFree(ctx->d_stage_norm));
+    ctx->d_stage_emb = nullptr; ctx->d_stage_norm = nullptr;
+    CK(cudaMalloc(&ctx->d_stage_emb, static_cast<size_t>(P) * 512 * 4));
+    CK(cudaMalloc(&ctx->d_stage_norm, static_cast<size_t>(P) * 4));
+    ctx->stage_emb_rows = P;
+  }
+  CK(cudaMemcpyAsync(ctx->d_stage_emb, h_probes, static_cast<size_t>(P) * 512 * 4, cudaMemcpyHostToDevice, st));
+  if (match_locked(ctx, ctx->d_stage_emb, P, k, thr, normalize, ctx->d_stage_sc, ctx->d_stage_idx, ctx->d_stage_acc,
+                   nullptr, st))
+    return 1;
+  CK(cudaMemcpyAsync(h_scores, ctx->d_stage_sc, static_cast<size_t>(P) * k * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_idx, ctx->d_stage_idx, static_cast<size_t>(P) * k * 8, cudaMemcpyDeviceToHost, st));
+  if (h_accept) CK(cudaMemcpyAsync(h_accept, ctx->d_stage_acc, P, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int frb_embed_match_host(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S, int flags, int k, float thr,
+                                    float* h_emb, float* h_scores, long long* h_idx, unsigned char* h_accept) {
+  if (!ctx) return 1;
+  if (B <= 0) return 0;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->own_stream;
+  if (embed_host_locked(ctx, h_rgb, B, S, flags, st)) return 1;
+  if (stage_match(ctx, B, k)) return 1;
+  // search() re-normalises the query (gallery_manager.py:195)
+  if (match_locked(ctx, ctx->d_stage_emb, B, k, thr, 1, ctx->d_stage_sc, ctx->d_stage_idx, ctx->d_stage_acc, nullptr, st))
+    return 1;
+  if (h_emb) CK(cudaMemcpyAsync(h_emb, ctx->d_stage_emb, static_cast<size_t>(B) * 512 * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_scores, ctx->d_stage_sc, static_cast<size_t>(B) * k * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_idx, ctx->d_stage_idx, static_cast<size_t>(B) * k * 8, cudaMemcpyDeviceToHost, st));
+  if (h_accept) CK(cudaMemcpyAsync(h_accept, ctx->d_stage_acc, B, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ====================================================================== test hooks
+extern "C" int frb_debug_gemm(frb_ctx* ctx, const void* d_A, const void* d_B, int M, int N, int K, int splits,
+                              float* d_C, void* stream) {
+  if (!ctx) return 1;
+  if (K % 64 || N % 64) return fail(ctx, "frb_debug_gemm: K and N must be multiples of 64");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  const int bn = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 64);
+  GemmParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.M = M; gp.N = N; gp.num_kb_main = K / 64; gp.num_kb_sc = 0;
+  gp.num_splits = choose_splits(gp.num_kb_main, std::max(1, splits));
+  if (gp.num_splits != 1 && gp.num_splits != splits) return fail(ctx, "frb_debug_gemm: splits=%d not realisable (got %d)", splits, gp.num_splits);
+  gp.out_f32 = d_C;
+  CUtensorMap a, b;
+  if (make_tmap_2d(ctx, &a, d_A, K, M, 128)) return 1;
+  if (make_tmap_2d(ctx, &b, d_B, K, N, bn)) return 1;
+  const int tiles = ((M + 127) / 128) * (N / bn) * gp.num_splits;
+  return launch_gemm(ctx, bn, A_TILED, a, a, b, gp, std::min(tiles, ctx->num_sms), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int frb_debug_conv(frb_ctx* ctx, const frb_layer_desc* L, int B, const void* d_in, const void* d_sc,
+                              const void* d_res, const void* d_w, const float* d_bias, const float* d_prelu,
+                              void* d_out, int use_ref, void* stream) {
+  if (!ctx || !L) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int P = out_dim(L->hin, L->ksize, L->stride, L->pad), Q = out_dim(L->win, L->ksize, L->stride, L->pad);
+  if (use_ref) {
+    ConvRefParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.in = reinterpret_cast<const __nv_bfloat16*>(d_in);
+    rp.sc = reinterpret_cast<const __nv_bfloat16*>(d_sc);
+    rp.wt = reinterpret_cast<const __nv_bfloat16*>(d_w);
+    rp.bias = d_bias; rp.bias_cases = L->bias_cases;
+    rp.prelu = L->has_prelu ? d_prelu : nullptr;
+    rp.residual = reinterpret_cast<const __nv_bfloat16*>(d_res);
+    rp.res_stride = L->res_stride; rp.RH = L->res_h; rp.RW = L->res_w;
+    rp.out = reinterpret_cast<__nv_bfloat16*>(d_out);
+    rp.B = B; rp.H = L->hin; rp.W = L->win; rp.Cin = L->cin; rp.Cout = L->cout; rp.P = P; rp.Q = Q;
+    rp.stride = L->stride; rp.ksize = L->ksize; rp.pad = L->pad;
+    rp.SH = L->sc_hin; rp.SW = L->sc_win; rp.Csc = d_sc ? L->sc_cin : 0; rp.sc_stride = L->sc_stride;
+    const size_t total = static_cast<size_t>(B) * P * Q * L->cout;
+    conv_ref_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(rp);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+  CUtensorMap a, a2, b;
+  GemmParams gp;
+  int bn, grid;
+  frb_layer_desc LL = *L;
+  if (!d_sc) { LL.sc_buf = -1; LL.sc_cin = 0; }
+  if (setup_conv(ctx, LL, B, d_in, d_sc, d_res, d_w, d_bias, d_prelu, d_out, &a, &a2, &b, &gp, &bn, &grid)) return 1;
+  return launch_gemm(ctx, bn, A_IM2COL, a, a2, b, gp, grid, st);
+}
+
+namespace {
+__global__ void im2col_dump_kernel(const __grid_constant__ CUtensorMap tm, int c, int w, int h, int n, int off_w,
+                                   int off_h, uint4* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, 16384);
+    tma_load_im2col_4d(&tm, bar, smem, c, w, h, n, static_cast<uint16_t>(off_w), static_cast<uint16_t>(off_h));
+  }
+  mbar_wait(bar, 0);
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = reinterpret_cast<uint4*>(smem)[i];
+}
+}  // namespace
+
+extern "C" int frb_debug_im2col(frb_ctx* ctx, const void* d_in, int B, int H, int W, int C, int ksize, int stride,
+                                int pad, int m0, int c0, int tap_r, int tap_s, void* d_out_16k, void* stream) {
+  if (!ctx) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CUtensorMap tm;
+  if (make_tmap_im2col(ctx, &tm, d_in, B, H, W, C, ksize, stride, pad)) return 1;
+  const int P = out_dim(H, ksize, stride, pad), Q = out_dim(W, ksize, stride, pad);
+  const int img = m0 / (P * Q), rem = m0 % (P * Q), pp = rem / Q, qq = rem % Q;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(im2col_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 64 + 1024));
+    attr_set = true;
+  }
+  im2col_dump_kernel<<<1, 128, 16384 + 64 + 1024, static_cast<cudaStream_t>(stream)>>>(
+      tm, c0, qq * stride - pad, pp * stride - pad, img, tap_s, tap_r, reinterpret_cast<uint4*>(d_out_16k));
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}

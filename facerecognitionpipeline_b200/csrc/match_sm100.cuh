@@ -1,0 +1,242 @@
+// match_sm100.cuh — gallery match: bf16 probe x gallery cosine GEMM on tcgen05 with a fused
+// per-row running top-k' in the epilogue, so the P x N score matrix never reaches HBM.
+//
+// Replaces the arithmetic of GalleryManager.search (reference gallery_manager.py:189-205:
+// normalise query, np.dot(G, q), argsort()[::-1][:k]) for P probes at once.
+//
+// Work item = (probe tile of 128 rows, gallery slice of consecutive 256-row tiles).
+// The probe tile (128 x 512 bf16 = 128 KB) stays resident in shared memory; gallery tiles
+// stream through a 3-stage TMA ring (32 KB per K block).  Each epilogue thread owns one probe
+// row (= one TMEM lane) and keeps that row's best kCand approximate scores of the slice in
+// registers.  A second kernel (match_finalize) merges the slices, re-scores the survivors
+// exactly from the fp32 gallery in f64, applies the canonical tie-break (score desc, index
+// asc) and proves, per row, that the bf16 filter cannot have dropped a true top-k entry
+// (rows failing the proof are re-done by the exact scan).
+#pragma once
+#include "ptx.cuh"
+
+namespace frb {
+
+constexpr int kMatchDim = 512;          // embedding size
+constexpr int kMatchKB = kMatchDim / 64;  // 8 K blocks
+constexpr int kMatchBN = 256;           // gallery rows per MMA tile
+constexpr int kCand = 8;                // candidates kept per (probe, slice)
+constexpr int kMatchBStages = 3;
+constexpr int kMatchThreads = 192;
+
+struct MatchParams {
+  int P;                 // probes
+  long long N;           // gallery rows held by this rank
+  int p_tiles;           // ceil(P / 128)
+  int g_tiles;           // ceil(N / 256)
+  int slices;            // gallery slices
+  int tiles_per_slice;   // ceil(g_tiles / slices)
+  float* cand_score;     // [P][slices][kCand]
+  int* cand_idx;         // [P][slices][kCand]  (local gallery row, -1 = empty)
+};
+
+struct MatchSmem {
+  static constexpr int kABytes = 128 * 64 * 2;       // one K block of the probe tile (16 KB)
+  static constexpr int kBBytes = kMatchBN * 64 * 2;  // one K block of a gallery tile (32 KB)
+  static constexpr int kTotal = kMatchKB * kABytes + kMatchBStages * kBBytes + 256 + 1024;
+};
+
+__device__ __forceinline__ void cand_insert(float (&ls)[kCand], int (&li)[kCand], float v, int idx) {
+  // caller guarantees v > ls[kCand-1]; strict '>' keeps the lower index on ties
+  ls[kCand - 1] = v;
+  li[kCand - 1] = idx;
+#pragma unroll
+  for (int i = kCand - 1; i > 0; --i) {
+    if (ls[i] > ls[i - 1]) {
+      const float ts = ls[i]; ls[i] = ls[i - 1]; ls[i - 1] = ts;
+      const int ti = li[i]; li[i] = li[i - 1]; li[i - 1] = ti;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMatchThreads, 1)
+match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmG,
+                    const MatchParams p) {
+  using S = MatchSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kMatchKB * S::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kMatchBStages * S::kBBytes);
+  uint64_t* a_full = bars;                    // 1
+  uint64_t* a_empty = bars + 1;               // 1
+  uint64_t* b_full = bars + 2;                // 3
+  uint64_t* b_empty = b_full + kMatchBStages; // 3
+  uint64_t* t_full = b_empty + kMatchBStages; // 2
+  uint64_t* t_empty = t_full + 2;             // 2
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_items = p.p_tiles * p.slices;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmP);
+    prefetch_tmap(&tmG);
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int i = 0; i < kMatchBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int pt = item % p.p_tiles;
+        const int gs = item / p.p_tiles;
+        const int t_begin = gs * p.tiles_per_slice;
+        const int t_end = min(p.g_tiles, t_begin + p.tiles_per_slice);
+        // probe tile: wait until the previous item's MMAs no longer read it
+        mbar_wait(a_empty, a_phase ^ 1);
+        mbar_arrive_expect_tx(a_full, kMatchKB * S::kABytes);
+        for (int kb = 0; kb < kMatchKB; ++kb)
+          tma_load_2d(&tmP, a_full, smem_a + kb * S::kABytes, kb * 64, pt * 128);
+        a_phase ^= 1;
+        for (int t = t_begin; t < t_end; ++t) {
+          for (int kb = 0; kb < kMatchKB; ++kb) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&b_full[stage], S::kBBytes);
+            tma_load_2d(&tmG, &b_full[stage], smem_b + stage * S::kBBytes, kb * 64, t * kMatchBN);
+            if (++stage == kMatchBStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, kMatchBN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int gs = item / p.p_tiles;
+        const int t_begin = gs * p.tiles_per_slice;
+        const int t_end = min(p.g_tiles, t_begin + p.tiles_per_slice);
+        mbar_wait(a_full, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(&t_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * kMatchBN;
+          for (int kb = 0; kb < kMatchKB; ++kb) {
+            mbar_wait(&b_full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + kb * S::kABytes));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * S::kBBytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&b_empty[stage]);
+            if (++stage == kMatchBStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(&t_full[acc]);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+        umma_commit(a_empty);  // all MMAs reading this probe tile have retired
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int pt = item % p.p_tiles;
+      const int gs = item / p.p_tiles;
+      const int t_begin = gs * p.tiles_per_slice;
+      const int t_end = min(p.g_tiles, t_begin + p.tiles_per_slice);
+      const int row = pt * 128 + quad * 32 + lane;
+      float ls[kCand];
+      int li[kCand];
+#pragma unroll
+      for (int i = 0; i < kCand; ++i) {
+        ls[i] = -INFINITY;
+        li[i] = -1;
+      }
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&t_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kMatchBN;
+        const long long col0 = static_cast<long long>(t) * kMatchBN;
+        const int ncols = static_cast<int>(min(static_cast<long long>(kMatchBN), p.N - col0));
+#pragma unroll 1
+        for (int c = 0; c < kMatchBN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (c * 32 >= ncols) continue;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = (c * 32 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY;
+          float m = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+          if (m > ls[kCand - 1]) {
+            const int base = static_cast<int>(col0) + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (v[j] > ls[kCand - 1]) cand_insert(ls, li, v[j], base + j);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (row < p.P) {
+        const size_t o = (static_cast<size_t>(row) * p.slices + gs) * kCand;
+        float4* ds = reinterpret_cast<float4*>(p.cand_score + o);
+        int4* di = reinterpret_cast<int4*>(p.cand_idx + o);
+        ds[0] = make_float4(ls[0], ls[1], ls[2], ls[3]);
+        ds[1] = make_float4(ls[4], ls[5], ls[6], ls[7]);
+        di[0] = make_int4(li[0], li[1], li[2], li[3]);
+        di[1] = make_int4(li[4], li[5], li[6], li[7]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace frb

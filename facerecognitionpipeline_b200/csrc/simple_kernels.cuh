@@ -1,0 +1,666 @@
+// simple_kernels.cuh — the bandwidth-bound / small kernels of the embed-and-match path:
+//   * warp_normalize : 5-landmark similarity warp (bit-exact restatement of cv2.warpAffine
+//                      INTER_LINEAR/BORDER_CONSTANT fixed-point arithmetic) fused with the
+//                      RGB->BGR + (x/255-0.5)/0.5 normalisation, emitting NHWC bf16
+//   * preprocess_u8  : FaceEmbedder.preprocess for already-aligned crops (112, or 224 -> 112)
+//   * stem_conv      : input_layer Conv3x3(3->64)+BN+PReLU (K = 27: CUDA-core direct conv)
+//   * conv_ref       : slow direct convolution used only by the tests as an on-device checker
+//   * fc_finalize    : split-K reduction + folded bias + L2 normalisation of the FC tail
+//   * match_finalize / exact scan : exact f64 re-scoring, canonical top-k, threshold
+#pragma once
+#include "ptx.cuh"
+
+namespace frb {
+
+// ------------------------------------------------------------------ warp + normalise
+// Per-face job. M is the FORWARD 2x3 matrix exactly as cv2.estimateAffinePartial2D returns it
+// (reference face_recognition.py:64); the kernel inverts it the way cv::warpAffine does.
+struct WarpJob {
+  unsigned long long src_off;  // byte offset of the source image from the base pointer
+  int H, W, pitch;             // source image geometry (pitch in bytes), RGB u8
+  int _pad;
+  double M[6];
+};
+
+// cv::warpAffine (imgwarp.cpp) constants
+constexpr int kAbBits = 10, kAbScale = 1 << kAbBits, kInterBits = 5, kInterTab = 1 << kInterBits;
+
+__device__ __forceinline__ int cv_round_sat(double v) {
+  // cv::saturate_cast<int>(double) == cvRound == lrint (round half to even), saturating
+  if (v >= 2147483647.0) return 2147483647;
+  if (v <= -2147483648.0) return (-2147483647 - 1);
+  return __double2int_rn(v);
+}
+
+// wtab: [32*32][4] int16 bilinear weights (sum exactly 32768), built on the host the way
+// cv::initInterTab2D builds BilinearTab_i.  lut: 256 bf16 bit patterns of the normalised value.
+template <bool kWriteU8, bool kWriteBf16>
+__global__ void __launch_bounds__(128)
+warp_normalize_kernel(const uint8_t* __restrict__ src_base, const WarpJob* __restrict__ jobs, int S,
+                      const short* __restrict__ wtab, const unsigned short* __restrict__ lut,
+                      uint8_t* __restrict__ out_u8, __nv_bfloat16* __restrict__ out_bf16) {
+  const int face = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= S * S) return;
+  const WarpJob jb = jobs[face];
+  // invert (double, unfused: mirrors the scalar C++ in cv::warpAffine / cv::invertAffineTransform)
+  double D = __dsub_rn(__dmul_rn(jb.M[0], jb.M[4]), __dmul_rn(jb.M[1], jb.M[3]));
+  D = (D != 0.0) ? __ddiv_rn(1.0, D) : 0.0;
+  const double A11 = __dmul_rn(jb.M[4], D), A22 = __dmul_rn(jb.M[0], D);
+  const double m00 = A11;
+  const double m01 = __dmul_rn(jb.M[1], -D);
+  const double m10 = __dmul_rn(jb.M[3], -D);
+  const double m11 = A22;
+  const double b1 = __dsub_rn(__dmul_rn(-m00, jb.M[2]), __dmul_rn(m01, jb.M[5]));
+  const double b2 = __dsub_rn(__dmul_rn(-m10, jb.M[2]), __dmul_rn(m11, jb.M[5]));
+
+  const int y = pix / S, x = pix - y * S;
+  const int round_delta = kAbScale / kInterTab / 2;
+  const int adelta = cv_round_sat(__dmul_rn(__dmul_rn(m00, (double)x), (double)kAbScale));
+  const int bdelta = cv_round_sat(__dmul_rn(__dmul_rn(m10, (double)x), (double)kAbScale));
+  const int X0 = cv_round_sat(__dmul_rn(__dadd_rn(__dmul_rn(m01, (double)y), b1), (double)kAbScale)) + round_delta;
+  const int Y0 = cv_round_sat(__dmul_rn(__dadd_rn(__dmul_rn(m11, (double)y), b2), (double)kAbScale)) + round_delta;
+  const int X = (X0 + adelta) >> (kAbBits - kInterBits);
+  const int Y = (Y0 + bdelta) >> (kAbBits - kInterBits);
+  const int sx = X >> kInterBits, sy = Y >> kInterBits;
+  const int ax = X & (kInterTab - 1), ay = Y & (kInterTab - 1);
+  const short4 w = reinterpret_cast<const short4*>(wtab)[ay * kInterTab + ax];
+
+  const uint8_t* img = src_base + jb.src_off;
+  int acc0 = 0, acc1 = 0, acc2 = 0;
+  const bool x0ok = (sx >= 0 && sx < jb.W), x1ok = (sx + 1 >= 0 && sx + 1 < jb.W);
+  if (sy >= 0 && sy < jb.H) {
+    const uint8_t* rowp = img + static_cast<size_t>(sy) * jb.pitch;
+    if (x0ok) {
+      const uint8_t* q = rowp + 3 * sx;
+      acc0 += w.x * q[0]; acc1 += w.x * q[1]; acc2 += w.x * q[2];
+    }
+    if (x1ok) {
+      const uint8_t* q = rowp + 3 * (sx + 1);
+      acc0 += w.y * q[0]; acc1 += w.y * q[1]; acc2 += w.y * q[2];
+    }
+  }
+  if (sy + 1 >= 0 && sy + 1 < jb.H) {
+    const uint8_t* rowp = img + static_cast<size_t>(sy + 1) * jb.pitch;
+    if (x0ok) {
+      const uint8_t* q = rowp + 3 * sx;
+      acc0 += w.z * q[0]; acc1 += w.z * q[1]; acc2 += w.z * q[2];
+    }
+    if (x1ok) {
+      const uint8_t* q = rowp + 3 * (sx + 1);
+      acc0 += w.w * q[0]; acc1 += w.w * q[1]; acc2 += w.w * q[2];
+    }
+  }
+  // FixedPtCast<int, uchar, 15>: (v + 2^14) >> 15, saturated
+  const int r = min(255, max(0, (acc0 + (1 << 14)) >> 15));
+  const int g = min(255, max(0, (acc1 + (1 << 14)) >> 15));
+  const int b = min(255, max(0, (acc2 + (1 << 14)) >> 15));
+  const size_t o = (static_cast<size_t>(face) * S * S + pix) * 3;
+  if (kWriteU8) {
+    out_u8[o] = (uint8_t)r; out_u8[o + 1] = (uint8_t)g; out_u8[o + 2] = (uint8_t)b;
+  }
+  if (kWriteBf16) {  // model is fed BGR (reference face_embedder.py:99)
+    unsigned short* ob = reinterpret_cast<unsigned short*>(out_bf16) + o;
+    ob[0] = lut[b]; ob[1] = lut[g]; ob[2] = lut[r];
+  }
+}
+
+// ------------------------------------------------------------------ preprocess (aligned crops)
+// in: [B][S][S][3] RGB u8, S in {112, 224}.  224 -> 112 is cv2.resize INTER_LINEAR at exactly
+// 2x, which equals the 2x2 box mean rounded half up.  flip: also emit the horizontally flipped
+// crop as image B+b (flip-fusion, BASELINE config 5).
+__global__ void __launch_bounds__(256)
+preprocess_u8_kernel(const uint8_t* __restrict__ in, int B, int S, const unsigned short* __restrict__ lut,
+                     __nv_bfloat16* __restrict__ out, int flip) {
+  const size_t total = static_cast<size_t>(B) * 112 * 112;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int b = static_cast<int>(i / (112 * 112));
+  const int pix = static_cast<int>(i - static_cast<size_t>(b) * 112 * 112);
+  const int y = pix / 112, x = pix - y * 112;
+  int r, g, bl;
+  if (S == 112) {
+    const uint8_t* q = in + (static_cast<size_t>(b) * 112 * 112 + pix) * 3;
+    r = q[0]; g = q[1]; bl = q[2];
+  } else {
+    const uint8_t* q0 = in + ((static_cast<size_t>(b) * 224 + 2 * y) * 224 + 2 * x) * 3;
+    const uint8_t* q1 = q0 + 224 * 3;
+    r = (q0[0] + q0[3] + q1[0] + q1[3] + 2) >> 2;
+    g = (q0[1] + q0[4] + q1[1] + q1[4] + 2) >> 2;
+    bl = (q0[2] + q0[5] + q1[2] + q1[5] + 2) >> 2;
+  }
+  unsigned short* o = reinterpret_cast<unsigned short*>(out);
+  const size_t d = (static_cast<size_t>(b) * 112 * 112 + pix) * 3;
+  o[d] = lut[bl]; o[d + 1] = lut[g]; o[d + 2] = lut[r];
+  if (flip) {
+    const size_t f = ((static_cast<size_t>(B + b) * 112 + y) * 112 + (111 - x)) * 3;
+    o[f] = lut[bl]; o[f + 1] = lut[g]; o[f + 2] = lut[r];
+  }
+}
+
+// ------------------------------------------------------------------ stem conv 3 -> 64
+// in: [B][112][112][3] bf16, w: [27][64] fp32 (tap-major, BN folded), out: [B][112][112][64] bf16.
+// One block = 16x16 output pixels; one thread = one pixel x 64 channels.
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                 const float* __restrict__ bias, const float* __restrict__ prelu,
+                 __nv_bfloat16* __restrict__ out, int H, int W) {
+  __shared__ float s_in[18][18][3];
+  __shared__ __align__(16) float s_w[27][64];
+  __shared__ __align__(16) float s_bias[64];
+  __shared__ __align__(16) float s_prelu[64];
+  const int img = blockIdx.z;
+  const int ty0 = blockIdx.y * 16, tx0 = blockIdx.x * 16;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * 64; i += 256) (&s_w[0][0])[i] = w[i];
+  if (tid < 64) {
+    s_bias[tid] = bias[tid];
+    s_prelu[tid] = prelu[tid];
+  }
+  const __nv_bfloat16* src = in + static_cast<size_t>(img) * H * W * 3;
+  for (int i = tid; i < 18 * 18 * 3; i += 256) {
+    const int c = i % 3, xx = (i / 3) % 18, yy = i / 54;
+    const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __bfloat162float(src[(static_cast<size_t>(gy) * W + gx) * 3 + c]);
+    s_in[yy][xx][c] = v;
+  }
+  __syncthreads();
+  const int ly = tid >> 4, lx = tid & 15;
+  const int oy = ty0 + ly, ox = tx0 + lx;
+  float acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    const int tap = t / 3, c = t - tap * 3;
+    const int r = tap / 3, s = tap - r * 3;
+    const float x = s_in[ly + r][lx + s][c];
+    const float4* wr = reinterpret_cast<const float4*>(&s_w[t][0]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 ww = wr[j];
+      acc[4 * j] = fmaf(x, ww.x, acc[4 * j]);
+      acc[4 * j + 1] = fmaf(x, ww.y, acc[4 * j + 1]);
+      acc[4 * j + 2] = fmaf(x, ww.z, acc[4 * j + 2]);
+      acc[4 * j + 3] = fmaf(x, ww.w, acc[4 * j + 3]);
+    }
+  }
+  if (oy < H && ox < W) {
+    uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * H + oy) * W + ox) * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        float a = acc[8 * j + t] + s_bias[8 * j + t];
+        v[t] = a > 0.f ? a : a * s_prelu[8 * j + t];
+      }
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      dst[j] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ reference conv (tests only)
+// Same contract as the tcgen05 implicit-GEMM conv (GemmParams semantics), one thread per output
+// element, fp32 accumulate in K order.  Used by tests as an on-device checker for big shapes.
+struct ConvRefParams {
+  const __nv_bfloat16* in;   // [B][H][W][Cin]
+  const __nv_bfloat16* sc;   // [B][SH][SW][Csc] or nullptr
+  const __nv_bfloat16* wt;   // [Cout][taps*Cin + Csc]
+  const float* bias; int bias_cases;
+  const float* prelu;
+  const __nv_bfloat16* residual; int res_stride, RH, RW;
+  __nv_bfloat16* out;        // [B][P][Q][Cout]
+  int B, H, W, Cin, Cout, P, Q, stride, ksize, pad;
+  int SH, SW, Csc, sc_stride;
+};
+
+__global__ void conv_ref_kernel(const ConvRefParams p) {
+  const size_t total = static_cast<size_t>(p.B) * p.P * p.Q * p.Cout;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % p.Cout);
+  const size_t m = i / p.Cout;
+  const int qq = static_cast<int>(m % p.Q);
+  const int pp = static_cast<int>((m / p.Q) % p.P);
+  const int img = static_cast<int>(m / (static_cast<size_t>(p.P) * p.Q));
+  const int Ktot = p.ksize * p.ksize * p.Cin + p.Csc;
+  const __nv_bfloat16* wrow = p.wt + static_cast<size_t>(co) * Ktot;
+  float acc = 0.f;
+  for (int r = 0; r < p.ksize; ++r)
+    for (int s = 0; s < p.ksize; ++s) {
+      const int iy = pp * p.stride - p.pad + r, ix = qq * p.stride - p.pad + s;
+      if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
+      const __nv_bfloat16* x = p.in + ((static_cast<size_t>(img) * p.H + iy) * p.W + ix) * p.Cin;
+      const __nv_bfloat16* ww = wrow + (r * p.ksize + s) * p.Cin;
+      for (int c = 0; c < p.Cin; ++c) acc = fmaf(__bfloat162float(x[c]), __bfloat162float(ww[c]), acc);
+    }
+  if (p.sc != nullptr) {
+    const __nv_bfloat16* x = p.sc + ((static_cast<size_t>(img) * p.SH + pp * p.sc_stride) * p.SW + qq * p.sc_stride) * p.Csc;
+    const __nv_bfloat16* ww = wrow + p.ksize * p.ksize * p.Cin;
+    for (int c = 0; c < p.Csc; ++c) acc = fmaf(__bfloat162float(x[c]), __bfloat162float(ww[c]), acc);
+  }
+  int bc = 0;
+  if (p.bias_cases == 9) {
+    const int rc = (pp == 0) ? 0 : ((pp == p.P - 1) ? 2 : 1);
+    const int cc = (qq == 0) ? 0 : ((qq == p.Q - 1) ? 2 : 1);
+    bc = rc * 3 + cc;
+  }
+  if (p.bias) acc += p.bias[static_cast<size_t>(bc) * p.Cout + co];
+  if (p.prelu) acc = acc > 0.f ? acc : acc * p.prelu[co];
+  if (p.residual)
+    acc += __bfloat162float(p.residual[((static_cast<size_t>(img) * p.RH + pp * p.res_stride) * p.RW + qq * p.res_stride) * p.Cout + co]);
+  p.out[i] = __float2bfloat16_rn(acc);
+}
+
+// ------------------------------------------------------------------ FC tail finalize
+// partial: [splits][B][512] fp32.  x = sum(partials) + bias; AdaFace: norm = ||x||2, emb = x/norm
+// (upstream net.py Backbone.forward).  l2 = 0 keeps the raw BN1d output (iresnet / ArcFace layout).
+// renorm = 1 applies FaceEmbedder's extra e/(||e||+1e-8) (reference face_embedder.py:133,178-180).
+__global__ void __launch_bounds__(128)
+fc_finalize_kernel(const float* __restrict__ partial, int splits, int B, const float* __restrict__ bias,
+                   int l2, int renorm, float* __restrict__ out_emb, float* __restrict__ out_norm,
+                   __nv_bfloat16* __restrict__ out_bf16) {
+  const int b = blockIdx.x;
+  const int t = threadIdx.x;
+  __shared__ float red[4];
+  float x[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = t + 128 * j;
+    float a = 0.f;
+    for (int s = 0; s < splits; ++s) a += partial[(static_cast<size_t>(s) * B + b) * 512 + n];
+    x[j] = a + bias[n];
+  }
+  auto block_norm = [&]() -> float {
+    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = ss;
+    __syncthreads();
+    return sqrtf(red[0] + red[1] + red[2] + red[3]);
+  };
+  float nrm = block_norm();
+  if (l2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = x[j] / nrm;
+  }
+  if (out_norm && t == 0) out_norm[b] = nrm;
+  if (renorm) {
+    const float n2 = block_norm() + 1e-8f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = x[j] / n2;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = t + 128 * j;
+    if (out_emb) out_emb[static_cast<size_t>(b) * 512 + n] = x[j];
+    if (out_bf16) out_bf16[static_cast<size_t>(b) * 512 + n] = __float2bfloat16_rn(x[j]);
+  }
+}
+
+// flip fusion (BASELINE config 5): rows b and B+b are the embeddings of a crop and its hflip,
+// each already L2-normalised; template = mean of the two, renormalised with +1e-8
+// (GalleryManager._aggregate_embeddings with n = 2: filter skipped, gallery_manager.py:297-317).
+__global__ void __launch_bounds__(128)
+flip_fuse_kernel(const float* __restrict__ emb2, int B, float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  __shared__ float red[4];
+  float x[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = t + 128 * j;
+    x[j] = (emb2[static_cast<size_t>(b) * 512 + n] + emb2[static_cast<size_t>(B + b) * 512 + n]) * 0.5f;
+  }
+  float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((t & 31) == 0) red[t >> 5] = ss;
+  __syncthreads();
+  const float n2 = sqrtf(red[0] + red[1] + red[2] + red[3]) + 1e-8f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = t + 128 * j;
+    const float v = x[j] / n2;
+    out[static_cast<size_t>(b) * 512 + n] = v;
+    if (out_bf16) out_bf16[static_cast<size_t>(b) * 512 + n] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------ probe / gallery prep
+// q = q / (||q|| + 1e-8)  (GalleryManager.search, gallery_manager.py:195), fp32, + bf16 copy
+__global__ void __launch_bounds__(128)
+probe_prepare_kernel(const float* __restrict__ in, int normalize, float* __restrict__ out_f32,
+                     __nv_bfloat16* __restrict__ out_bf16) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  __shared__ float red[4];
+  float x[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) x[j] = in[static_cast<size_t>(b) * 512 + t + 128 * j];
+  if (normalize) {
+    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((t & 31) == 0) red[t >> 5] = ss;
+    __syncthreads();
+    const float n2 = sqrtf(red[0] + red[1] + red[2] + red[3]) + 1e-8f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = x[j] / n2;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const size_t o = static_cast<size_t>(b) * 512 + t + 128 * j;
+    out_f32[o] = x[j];
+    out_bf16[o] = __float2bfloat16_rn(x[j]);
+  }
+}
+
+// fp32 gallery rows -> bf16 copy + per-block max row norm (for the filter's error bound)
+__global__ void __launch_bounds__(256)
+gallery_prepare_kernel(const float* __restrict__ g, long long N, __nv_bfloat16* __restrict__ gb,
+                       float* __restrict__ max_norm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  float nrm = 0.f;
+  if (row < N) {
+    const float4* src = reinterpret_cast<const float4*>(g + row * 512);
+    uint2* dst = reinterpret_cast<uint2*>(gb + row * 512);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v = src[lane + 32 * j];
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y);
+      o.y = pack_bf16x2(v.z, v.w);
+      dst[lane + 32 * j] = o;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    nrm = sqrtf(ss);
+  }
+  if (lane == 0 && row < N) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(nrm));  // nrm >= 0
+}
+
+// ------------------------------------------------------------------ exact scoring helpers
+// f64 dot of two fp32 rows of 512 by one warp: lane owns elements lane + 32*j, fixed order,
+// then a fixed xor-shuffle tree -> deterministic, identical for identical rows.
+__device__ __forceinline__ double warp_dot512_f64(const float* __restrict__ a, const float* __restrict__ b, int lane) {
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s = fma(static_cast<double>(a[lane + 32 * j]), static_cast<double>(b[lane + 32 * j]), s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// canonical order: score descending, then index ascending; idx < 0 sorts last
+__device__ __forceinline__ bool cand_before(double sa, long long ia, double sb, long long ib) {
+  if (ia < 0) return false;
+  if (ib < 0) return true;
+  if (sa != sb) return sa > sb;
+  return ia < ib;
+}
+
+constexpr int kRescore = 64;       // survivors re-scored exactly per probe
+constexpr int kMaxCandPad = 2048;  // >= slices * kCand, power of two
+
+struct FinalizeParams {
+  const float* cand_score; const int* cand_idx;  // [P][slices][kCand]
+  int slices;
+  const float* probes;   // [P][512] fp32 (already normalised as search() does)
+  const float* gallery;  // [N][512] fp32
+  long long N;
+  long long first_global_id;
+  int k;
+  float thr;
+  const float* max_norm;     // gallery max row norm (device scalar)
+  double* out_score;         // [P][k] f64
+  long long* out_idx;        // [P][k] global ids, -1 = none
+  float* out_score_f32;      // [P][k]
+  unsigned char* out_accept; // [P]  top-1 score >= thr
+  int* flagged;              // [P] 1 = proof failed -> exact scan required
+};
+
+// one block (128 threads) per probe
+__global__ void __launch_bounds__(128)
+match_finalize_kernel(const FinalizeParams p) {
+  __shared__ float s_sc[kMaxCandPad];
+  __shared__ int s_ix[kMaxCandPad];
+  __shared__ float s_probe[512];
+  __shared__ double s_ex[kRescore];
+  __shared__ long long s_exi[kRescore];
+  __shared__ float s_excl;
+  const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int C = p.slices * kCand;
+  int Cp = 64;
+  while (Cp < C) Cp <<= 1;
+  for (int i = t; i < Cp; i += 128) {
+    if (i < C) {
+      s_sc[i] = p.cand_score[static_cast<size_t>(row) * C + i];
+      s_ix[i] = p.cand_idx[static_cast<size_t>(row) * C + i];
+    } else {
+      s_sc[i] = -INFINITY;
+      s_ix[i] = -1;
+    }
+  }
+  for (int i = t; i < 512; i += 128) s_probe[i] = p.probes[static_cast<size_t>(row) * 512 + i];
+  if (t == 0) s_excl = -INFINITY;
+  __syncthreads();
+  // bound on every element a slice dropped: that slice's smallest kept score (if its list is full)
+  {
+    float mx = -INFINITY;
+    for (int s = t; s < p.slices; s += 128) {
+      const int last = s * kCand + kCand - 1;
+      if (s_ix[last] >= 0) mx = fmaxf(mx, s_sc[last]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __shared__ float s_mx[4];
+    if (lane == 0) s_mx[warp] = mx;
+    __syncthreads();
+    if (t == 0) s_excl = fmaxf(fmaxf(s_mx[0], s_mx[1]), fmaxf(s_mx[2], s_mx[3]));
+    __syncthreads();
+  }
+  // bitonic sort of the approximate candidates, canonical order
+  for (int k2 = 2; k2 <= Cp; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < Cp; i += 128) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = ((i & k2) == 0);
+          const bool i_first = cand_before(s_sc[i], s_ix[i], s_sc[l], s_ix[l]);
+          if (up ? !i_first : i_first) {
+            const float ts = s_sc[i]; s_sc[i] = s_sc[l]; s_sc[l] = ts;
+            const int ti = s_ix[i]; s_ix[i] = s_ix[l]; s_ix[l] = ti;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // exact re-score of the best kRescore survivors
+  for (int c = warp; c < kRescore; c += 4) {
+    const int gi = s_ix[c];
+    double sc = 0.0;
+    if (gi >= 0) sc = warp_dot512_f64(p.gallery + static_cast<size_t>(gi) * 512, s_probe, lane);
+    if (lane == 0) {
+      s_ex[c] = sc;
+      s_exi[c] = gi;
+    }
+  }
+  __syncthreads();
+  // sort the kRescore exact scores (bitonic, 64 elements, 128 threads)
+  for (int k2 = 2; k2 <= kRescore; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      if (t < kRescore) {
+        const int i = t, l = i ^ j;
+        if (l > i) {
+          const bool up = ((i & k2) == 0);
+          const bool i_first = cand_before(s_ex[i], s_exi[i], s_ex[l], s_exi[l]);
+          if (up ? !i_first : i_first) {
+            const double ts = s_ex[i]; s_ex[i] = s_ex[l]; s_ex[l] = ts;
+            const long long ti = s_exi[i]; s_exi[i] = s_exi[l]; s_exi[l] = ti;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (t < p.k) {
+    const long long gi = s_exi[t];
+    const size_t o = static_cast<size_t>(row) * p.k + t;
+    p.out_idx[o] = gi >= 0 ? gi + p.first_global_id : -1;
+    p.out_score[o] = gi >= 0 ? s_ex[t] : -INFINITY;
+    p.out_score_f32[o] = gi >= 0 ? static_cast<float>(s_ex[t]) : -INFINITY;
+  }
+  if (t == 0) {
+    p.out_accept[row] = (s_exi[0] >= 0 && static_cast<float>(s_ex[0]) >= p.thr) ? 1 : 0;
+    // Proof that the bf16 filter dropped nothing from the true top-k:
+    // anything not re-scored has approx score <= bound, hence exact score <= bound + eps.
+    const int kk = static_cast<int>(min(static_cast<long long>(p.k), p.N));
+    int flag = 0;
+    if (kk > 0) {
+      float bound = s_excl;
+      if (Cp > kRescore && s_ix[kRescore] >= 0) bound = fmaxf(bound, s_sc[kRescore]);
+      if (bound > -INFINITY) {
+        float pn = 0.f;
+        for (int i = 0; i < 512; ++i) pn += s_probe[i] * s_probe[i];
+        const float eps = (0.0078125f + 0.000244140625f) * sqrtf(pn) * (*p.max_norm) * 1.0001f + 1e-6f;
+        if (s_exi[kk - 1] < 0 || s_ex[kk - 1] <= static_cast<double>(bound) + eps) flag = 1;
+      }
+    }
+    p.flagged[row] = flag;
+  }
+}
+
+// Exact scan: dense f64 scores of F listed probes against the whole local gallery.
+// grid.x covers gallery rows (8 warps -> 8 rows per block iteration), grid.y = probe in list.
+__global__ void __launch_bounds__(256)
+match_exact_scores_kernel(const float* __restrict__ gallery, long long N, const float* __restrict__ probes,
+                          const int* __restrict__ rows, double* __restrict__ scores) {
+  __shared__ float s_probe[512];
+  const int f = blockIdx.y;
+  const int prow = rows ? rows[f] : f;
+  for (int i = threadIdx.x; i < 512; i += 256) s_probe[i] = probes[static_cast<size_t>(prow) * 512 + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long g = static_cast<long long>(blockIdx.x) * 8 + warp; g < N; g += static_cast<long long>(gridDim.x) * 8) {
+    const double s = warp_dot512_f64(gallery + g * 512, s_probe, lane);
+    if (lane == 0) scores[static_cast<size_t>(f) * N + g] = s;
+  }
+}
+
+// top-k of a dense f64 score row by k rounds of block arg-max (canonical order); one block per row.
+__global__ void __launch_bounds__(256)
+match_exact_topk_kernel(const double* __restrict__ scores, long long N, const int* __restrict__ rows, int k,
+                        float thr, long long first_global_id, double* __restrict__ out_score,
+                        long long* __restrict__ out_idx, float* __restrict__ out_score_f32,
+                        unsigned char* __restrict__ out_accept) {
+  __shared__ double s_best[256];
+  __shared__ long long s_besti[256];
+  __shared__ double s_prev;
+  __shared__ long long s_previ;
+  const int f = blockIdx.x, t = threadIdx.x;
+  const int prow = rows ? rows[f] : f;
+  const double* sc = scores + static_cast<size_t>(f) * N;
+  if (t == 0) {
+    s_prev = INFINITY;
+    s_previ = -1;
+  }
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    const double pv = s_prev;
+    const long long pi = s_previ;
+    double best = -INFINITY;
+    long long besti = -1;
+    for (long long g = t; g < N; g += 256) {
+      const double v = sc[g];
+      // strictly after (pv, pi) in canonical order
+      const bool after = (pi < 0) ? true : ((v < pv) || (v == pv && g > pi));
+      if (after && cand_before(v, g, best, besti)) {
+        best = v;
+        besti = g;
+      }
+    }
+    s_best[t] = best;
+    s_besti[t] = besti;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (t < o && cand_before(s_best[t + o], s_besti[t + o], s_best[t], s_besti[t])) {
+        s_best[t] = s_best[t + o];
+        s_besti[t] = s_besti[t + o];
+      }
+      __syncthreads();
+    }
+    if (t == 0) {
+      const size_t o = static_cast<size_t>(prow) * k + r;
+      const long long gi = s_besti[0];
+      out_idx[o] = gi >= 0 ? gi + first_global_id : -1;
+      out_score[o] = gi >= 0 ? s_best[0] : -INFINITY;
+      out_score_f32[o] = gi >= 0 ? static_cast<float>(s_best[0]) : -INFINITY;
+      if (r == 0) out_accept[prow] = (gi >= 0 && static_cast<float>(s_best[0]) >= thr) ? 1 : 0;
+      s_prev = s_best[0];
+      s_previ = gi;
+    }
+    __syncthreads();
+    if (s_previ < 0) {  // gallery exhausted: fill the rest
+      if (t == 0)
+        for (int r2 = r + 1; r2 < k; ++r2) {
+          const size_t o = static_cast<size_t>(prow) * k + r2;
+          out_idx[o] = -1; out_score[o] = -INFINITY; out_score_f32[o] = -INFINITY;
+        }
+      break;
+    }
+  }
+}
+
+// merge G per-rank top-k lists (after an all-gather) into the global top-k; one thread per probe.
+// in_score/in_idx: [G][P][k]
+__global__ void topk_merge_kernel(const double* __restrict__ in_score, const long long* __restrict__ in_idx, int G,
+                                  int P, int k, float thr, double* __restrict__ out_score,
+                                  long long* __restrict__ out_idx, float* __restrict__ out_score_f32,
+                                  unsigned char* __restrict__ out_accept) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= P) return;
+  double ps = INFINITY;
+  long long pi = -1;
+  for (int r = 0; r < k; ++r) {
+    double best = -INFINITY;
+    long long besti = -1;
+    for (int g = 0; g < G; ++g)
+      for (int j = 0; j < k; ++j) {
+        const size_t o = (static_cast<size_t>(g) * P + row) * k + j;
+        const double v = in_score[o];
+        const long long ix = in_idx[o];
+        if (ix < 0) continue;
+        const bool after = (pi < 0) ? true : ((v < ps) || (v == ps && ix > pi));
+        if (after && cand_before(v, ix, best, besti)) {
+          best = v;
+          besti = ix;
+        }
+      }
+    const size_t o = static_cast<size_t>(row) * k + r;
+    out_idx[o] = besti;
+    out_score[o] = besti >= 0 ? best : -INFINITY;
+    out_score_f32[o] = besti >= 0 ? static_cast<float>(best) : -INFINITY;
+    if (r == 0) out_accept[row] = (besti >= 0 && static_cast<float>(best) >= thr) ? 1 : 0;
+    if (besti < 0) {
+      for (int r2 = r + 1; r2 < k; ++r2) {
+        const size_t o2 = static_cast<size_t>(row) * k + r2;
+        out_idx[o2] = -1; out_score[o2] = -INFINITY; out_score_f32[o2] = -INFINITY;
+      }
+      break;
+    }
+    ps = best;
+    pi = besti;
+  }
+}
+
+}  // namespace frb

@@ -1,0 +1,133 @@
+/* frb200.h — C ABI of libfrb200.so: the B200 (sm_100a) embed-and-match hot path behind the
+ * FaceRecognitionPipeline API.
+ *
+ * The reference is pure Python and has no FFI; the seams this ABI replaces are the library calls
+ * its hot path makes (all citations into the reference tree):
+ *   - face_recognition.py:61-75   FaceAligner.align -> cv2.warpAffine          => frb_warp_normalize
+ *   - face_embedder.py:93-110     FaceEmbedder.preprocess (resize/BGR/normalise) => frb_preprocess_u8
+ *   - face_embedder.py:49-56      net.build_model + load_state_dict             => frb_backbone_load
+ *   - face_embedder.py:119,157    self.model(x) -> (features, norm)             => frb_embed
+ *   - face_embedder.py:132-133,178-180  e / (||e|| + 1e-8)                     => frb_embed(flags RENORM)
+ *   - gallery_manager.py:177-187  get_gallery_embeddings (np.vstack per query)  => frb_gallery_upload (once)
+ *   - gallery_manager.py:189-205  search: normalise q, np.dot, argsort top-k    => frb_match
+ *   - face_matcher.py:205         score >= similarity_threshold                 => frb_match accept[]
+ *   (new, no reference counterpart) identity-sharded gallery merge              => frb_topk_merge
+ *
+ * Conventions: every call returns 0 on success, non-zero on failure (message via
+ * frb_last_error).  No exceptions, no Python objects, no torch types cross this boundary.
+ * Pointers named d_* are CUDA device pointers owned by the caller; h_* are host pointers.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  A ctx is bound to
+ * one device and serialises its own calls with an internal mutex (the reference is called
+ * concurrently under Flask threaded=True, face_recognition_server.py:1102).
+ */
+#ifndef FRB200_H
+#define FRB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct frb_ctx frb_ctx;
+
+#define FRB_OP_STEM 0 /* Conv3x3(3->64)+BN+PReLU, direct */
+#define FRB_OP_CONV 1 /* implicit-GEMM conv (3x3 or 1x1) with fused epilogue */
+#define FRB_OP_FC 2   /* BN2d-Flatten-Linear-BN1d folded into one GEMM + L2 norm */
+
+#define FRB_EMBED_L2 1     /* model L2-normalises its output (AdaFace Backbone.forward) */
+#define FRB_EMBED_RENORM 2 /* apply FaceEmbedder's extra e/(||e||+1e-8) (normalize=True) */
+#define FRB_EMBED_FLIP 4   /* input holds 2B crops (orig, hflip): fuse pairs -> B embeddings */
+
+/* One step of the backbone program.  The host side (weights.py) folds BatchNorm into the
+ * weights/biases, orders K as (tap, cin) [+ shortcut cin] and assigns activation buffers. */
+typedef struct frb_layer_desc {
+  int32_t op;
+  int32_t cin, cout;
+  int32_t hin, win;           /* input spatial size */
+  int32_t ksize, stride, pad; /* 3/1, 1|2, 1/0 */
+  int32_t in_buf, out_buf;    /* activation buffer ids; in_buf = -1 means the network input */
+  int32_t sc_buf, sc_cin, sc_hin, sc_win, sc_stride; /* fused 1x1 shortcut conv source; sc_buf < 0: none */
+  int32_t res_buf, res_h, res_w, res_stride;         /* identity (MaxPool(1,stride)) shortcut; res_buf < 0: none */
+  int32_t bias_cases;         /* 1, or 9 = border-position table (pre-activation BN under zero padding) */
+  int32_t has_prelu;
+  int32_t reserved[2];
+  int64_t w_off, w_bytes;     /* bf16 [cout][ktot] (CONV/FC) or f32 [27][64] (STEM) inside the blob */
+  int64_t bias_off;           /* f32 [bias_cases][cout] */
+  int64_t prelu_off;          /* f32 [cout] (ignored unless has_prelu) */
+} frb_layer_desc;
+
+/* Per-face warp job: forward 2x3 matrix as cv2.estimateAffinePartial2D returns it. */
+typedef struct frb_warp_job {
+  uint64_t src_off; /* byte offset of this face's source image from d_src_base */
+  int32_t H, W, pitch;
+  int32_t _pad;
+  double M[6];
+} frb_warp_job;
+
+int frb_ctx_create(int device, frb_ctx** out);
+void frb_ctx_destroy(frb_ctx* ctx);
+const char* frb_last_error(frb_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+long long frb_launch_count(frb_ctx* ctx);
+
+/* ---- preprocessing ---- */
+/* d_in: [B][S][S][3] RGB u8, S in {112,224}; d_out: [B (2B if flip)][112][112][3] bf16 BGR normalised */
+int frb_preprocess_u8(frb_ctx* ctx, const void* d_in, int B, int S, void* d_out, int flip, void* stream);
+/* jobs on the HOST (copied inside); S = output size; either output may be NULL.
+ * d_out_u8: [B][S][S][3] RGB u8 (== FaceAligner.align); d_out_bf16: [B][112][112][3] (S must be 112) */
+int frb_warp_normalize(frb_ctx* ctx, const void* d_src_base, const frb_warp_job* h_jobs, int B, int S,
+                       void* d_out_u8, void* d_out_bf16, void* stream);
+
+/* ---- backbone ---- */
+int frb_backbone_load(frb_ctx* ctx, const frb_layer_desc* layers, int n_layers, const void* h_blob,
+                      size_t blob_bytes, int n_bufs);
+/* d_in: [B'][112][112][3] bf16 (B' = 2B with FRB_EMBED_FLIP); outputs [B][512] f32, [B] f32, [B][512] bf16;
+ * any output may be NULL. */
+int frb_embed(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, float* d_norm,
+              void* d_emb_bf16, void* stream);
+double frb_backbone_flops_per_face(frb_ctx* ctx);
+
+/* ---- gallery ---- */
+/* g: [N][512] f32 rows (NOT re-normalised, as in search()); is_device selects the pointer kind.
+ * first_global_id is added to local row numbers in every result (identity-sharded galleries). */
+int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, long long first_global_id, int is_device);
+long long frb_gallery_size(frb_ctx* ctx);
+/* d_probes: [P][512] f32.  normalize != 0 applies q/(||q||+1e-8) first (search()).
+ * Outputs (device): scores f32 [P][k], idx i64 [P][k] (global ids, -1 = fewer than k rows),
+ * accept u8 [P] (top-1 score >= thr), scores64 f64 [P][k] (optional, for cross-rank merge). */
+int frb_match(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, int normalize,
+              float* d_scores, long long* d_idx, unsigned char* d_accept, double* d_scores64, void* stream);
+/* how many probes of the last frb_match needed the exact re-scan (filter proof failed) */
+int frb_match_last_flagged(frb_ctx* ctx);
+/* merge G gathered per-rank top-k lists: in [G][P][k] -> out [P][k] */
+int frb_topk_merge(frb_ctx* ctx, const double* d_in_scores64, const long long* d_in_idx, int G, int P, int k,
+                   float thr, float* d_scores, long long* d_idx, unsigned char* d_accept, double* d_scores64,
+                   void* stream);
+
+/* ---- host-buffer entry points (what the Python drop-in calls; copies happen inside) ---- */
+/* h_rgb: [B][S][S][3] u8 -> h_emb [B][512] f32 (+ h_norm [B] optional) */
+int frb_embed_host(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S, int flags, float* h_emb, float* h_norm);
+/* h_probes [P][512] f32 -> h_scores [P][k], h_idx [P][k], h_accept [P] */
+int frb_match_host(frb_ctx* ctx, const float* h_probes, int P, int k, float thr, int normalize,
+                   float* h_scores, long long* h_idx, unsigned char* h_accept);
+/* whole path: aligned crops -> embed -> match against the uploaded gallery */
+int frb_embed_match_host(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S, int flags, int k, float thr,
+                         float* h_emb, float* h_scores, long long* h_idx, unsigned char* h_accept);
+
+/* ---- test hooks (used by tests/ only) ---- */
+/* C[M][N] f32 = A[M][K] * B[N][K]^T, bf16 inputs, K % 64 == 0, N % 64 == 0 */
+int frb_debug_gemm(frb_ctx* ctx, const void* d_A, const void* d_B, int M, int N, int K, int splits,
+                   float* d_C, void* stream);
+/* single conv layer through the tcgen05 path (use_ref = 0) or the direct checker (use_ref = 1) */
+int frb_debug_conv(frb_ctx* ctx, const frb_layer_desc* layer, int B, const void* d_in, const void* d_sc,
+                   const void* d_res, const void* d_w, const float* d_bias, const float* d_prelu,
+                   void* d_out, int use_ref, void* stream);
+/* raw im2col-mode TMA tile (128 pixels x 64 channels, swizzled as landed) for inspection */
+int frb_debug_im2col(frb_ctx* ctx, const void* d_in, int B, int H, int W, int C, int ksize, int stride, int pad,
+                     int m0, int c0, int tap_r, int tap_s, void* d_out_16k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRB200_H */
