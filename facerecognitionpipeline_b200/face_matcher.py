@@ -1,0 +1,236 @@
+"""Drop-in for the reference `face_matcher.FaceMatcher` (face_matcher.py:19-385).
+
+`match_single_face` (face_matcher.py:52-58) is the per-face unit of the hot path: embed -> search.
+Here both halves run on the B200 in one C-ABI call (`frb_embed_match_host`), and
+`match_faces_batch` (new) does it for a whole list of crops at once.  The multi-frame consensus
+(`_aggregate_matches`, face_matcher.py:321-363) and result dictionaries are host glue with the
+reference's exact decision rules and field names.
+"""
+from __future__ import annotations
+
+import json
+import os
+from collections import Counter
+from datetime import datetime
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .face_embedder import FaceEmbedder
+from .gallery_manager import GalleryManager
+
+SCRIPT_DIR = Path(__file__).resolve().parent
+
+MIN_QUALITY_SCORE = 0.55   # face_matcher.py:324,366
+MIN_QUALITY_FRAMES = 3     # face_matcher.py:325
+
+
+def consensus(frame_matches: List[Dict], similarity_threshold: float) -> Optional[Dict]:
+    """Track-level decision of FaceMatcher._aggregate_matches: frames scoring >= 0.55 vote; at least 3
+    of them; the winner needs > 50 % of the votes, or > 40 % and at least twice the runner-up; the
+    mean of the winner's frame scores must reach the similarity threshold."""
+    voters = [m for m in frame_matches if m["score"] >= MIN_QUALITY_SCORE]
+    if len(voters) < MIN_QUALITY_FRAMES:
+        return None
+    ranking = Counter(m["student_id"] for m in voters).most_common(2)
+    winner, votes = ranking[0]
+    share = votes / len(voters)
+    agreed = share > 0.5
+    if not agreed and len(ranking) > 1:
+        agreed = share > 0.4 and votes >= 2 * ranking[1][1]
+    if not agreed:
+        return None
+    winner_scores = [m["score"] for m in voters if m["student_id"] == winner]
+    mean_score = np.mean(winner_scores)
+    if mean_score < similarity_threshold:
+        return None
+    return {
+        "student_id": winner,
+        "name": next(m["name"] for m in voters if m["student_id"] == winner),
+        "confidence": float(mean_score),
+        "consensus_strength": float(share),
+        "num_quality_frames": len(winner_scores),
+        "total_frames_evaluated": len(frame_matches),
+    }
+
+
+def best_candidate(frame_matches: List[Dict]) -> Dict:
+    """FaceMatcher._get_best_candidate (face_matcher.py:365-385)."""
+    pool = [m for m in frame_matches if m["score"] >= MIN_QUALITY_SCORE] or frame_matches
+    sid = Counter(m["student_id"] for m in pool).most_common(1)[0][0]
+    scores = [m["score"] for m in pool if m["student_id"] == sid]
+    return {
+        "student_id": sid,
+        "name": next(m["name"] for m in pool if m["student_id"] == sid),
+        "confidence": float(np.mean(scores)),
+        "num_quality_frames": len(scores),
+    }
+
+
+class FaceMatcher:
+    def __init__(self, gallery_path=None, similarity_threshold=0.5, aggregation_method="majority_vote",
+                 model_type="adaface", architecture="ir_101", embedder: Optional[FaceEmbedder] = None,
+                 gallery: Optional[GalleryManager] = None):
+        self.similarity_threshold = similarity_threshold
+        self.aggregation_method = aggregation_method
+        self.model_type = model_type
+        self.architecture = architecture
+        if gallery_path is None:
+            gallery_path = str(SCRIPT_DIR / "gallery" / "students.pkl")
+        print("Initializing Face Matcher...")
+        self.embedder = embedder if embedder is not None else FaceEmbedder(architecture=architecture, model_type=model_type)
+        self.gallery = gallery if gallery is not None else GalleryManager(gallery_path=gallery_path)
+        n = len(self.gallery.get_all_students())
+        if n == 0:
+            print("\nWARNING: Gallery is empty! Please enroll students first.")
+        else:
+            print(f"   Loaded {n} enrolled students")
+        print("Face Matcher ready!")
+
+    # ------------------------------------------------------------------ hot path
+    def match_faces_batch(self, face_images: List[np.ndarray], top_k: int = 5):
+        """Embed + match a list of aligned RGB crops.  Returns (results, accept): results[i] is what
+        match_single_face(face_images[i]) returns, accept[i] = top-1 score >= similarity_threshold."""
+        if len(face_images) == 0:
+            return [], np.zeros(0, dtype=bool)
+        embeddings = self.embedder.extract_embeddings_batch(face_images, normalize=True)
+        return self.gallery.search_batch(embeddings, top_k=top_k, threshold=self.similarity_threshold)
+
+    def match_single_face(self, face_image: np.ndarray, top_k: int = 5) -> List[Tuple[str, str, float]]:
+        embedding = self.embedder.extract_embedding(face_image, normalize=True)
+        return self.gallery.search(embedding, top_k=top_k)
+
+    # ------------------------------------------------------------------ track flow
+    def match_track(self, track_dir: str, top_k: int = 3) -> Optional[Dict]:
+        import cv2
+        track_id = os.path.basename(track_dir)
+        meta_path = os.path.join(track_dir, "metadata.json")
+        if not os.path.exists(meta_path):
+            print(f"No metadata found for {track_id}")
+            return None
+        with open(meta_path, "r") as f:
+            metadata = json.load(f)
+        files = sorted(f for f in os.listdir(track_dir) if f.endswith(".jpg"))
+        if not files:
+            print(f"No face images found in {track_id}")
+            return None
+        print(f"\nProcessing {track_id}: {len(files)} frames")
+        crops, names = [], []
+        for fn in files:
+            bgr = cv2.imread(os.path.join(track_dir, fn))
+            if bgr is None:
+                continue
+            crops.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))
+            names.append(fn)
+        results, _ = self.match_faces_batch(crops, top_k=top_k)
+        frame_matches = []
+        for fn, matches in zip(names, results):
+            if not matches:
+                continue
+            sid, name, score = matches[0]
+            frame_matches.append({
+                "frame": fn, "student_id": sid, "name": name, "score": float(score),
+                "top_k_matches": [{"student_id": s, "name": n, "score": float(v)} for s, n, v in matches],
+            })
+        if not frame_matches:
+            print("No valid matches found")
+            return None
+        all_scores: Dict[str, List[float]] = {}
+        for m in frame_matches:
+            all_scores.setdefault(m["student_id"], []).append(m["score"])
+        final = self._aggregate_matches(frame_matches, all_scores)
+        if final is None:
+            cand = self._get_best_candidate(frame_matches, all_scores)
+            print(f"Below threshold - Best candidate: {cand['name']} ({cand['student_id']}) - confidence: {cand['confidence']:.3f}")
+            return {"track_id": track_id, "recognized": False, "reason": "below_threshold", "best_candidate": cand,
+                    "frame_matches": frame_matches, "metadata": metadata, "timestamp": datetime.now().isoformat()}
+        print(f"  Identified: {final['name']} ({final['student_id']}) - confidence: {final['confidence']:.3f}")
+        return {"track_id": track_id, "recognized": True, "student_id": final["student_id"], "name": final["name"],
+                "confidence": final["confidence"], "method": self.aggregation_method, "num_frames": len(frame_matches),
+                "frame_matches": frame_matches, "metadata": metadata, "timestamp": datetime.now().isoformat()}
+
+    def _aggregate_matches(self, frame_matches: List[Dict], all_scores: Dict[str, List[float]]) -> Optional[Dict]:
+        return consensus(frame_matches, self.similarity_threshold)
+
+    def _get_best_candidate(self, frame_matches, all_scores):
+        return best_candidate(frame_matches)
+
+    # ------------------------------------------------------------------ single image flow
+    def match_single_image(self, image_path: str, top_k: int = 5, save_visualization: bool = True) -> Dict:
+        if not os.path.exists(image_path):
+            raise ValueError(f"Image not found: {image_path}")
+        from .face_recognition import FaceProcessor  # needs insightface for detection (out of scope here)
+        processor = FaceProcessor(output_size=112, det_size=(640, 640), det_thresh=0.5, quality_filter_config={
+            "min_det_score": 0.5, "min_face_size": 40, "max_yaw": 60, "max_pitch": 45, "max_roll": 45,
+            "check_blur": True, "blur_threshold": 50}, providers=["CUDAExecutionProvider", "CPUExecutionProvider"])
+        faces = processor.process_image(image_path, return_all=True)
+        if not faces:
+            print("No faces detected in image")
+            return {"image_path": image_path, "num_faces": 0, "matches": [], "timestamp": datetime.now().isoformat()}
+        results, accept = self.match_faces_batch([f["aligned_face"] for f in faces], top_k=top_k)
+        matches = []
+        for idx, (face, res, ok) in enumerate(zip(faces, results, accept)):
+            if not res:
+                matches.append({"face_index": idx, "bbox": face["bbox"].tolist(), "recognized": False,
+                                "reason": "no_gallery_matches", "quality_metrics": face["quality_metrics"]})
+                continue
+            sid, name, score = res[0]
+            recognized = bool(score >= self.similarity_threshold)
+            entry = {"face_index": idx, "bbox": face["bbox"].tolist(), "recognized": recognized,
+                     "confidence": float(score), "quality_metrics": face["quality_metrics"],
+                     "top_matches": [{"student_id": s, "name": n, "score": float(v), "rank": r + 1}
+                                     for r, (s, n, v) in enumerate(res)]}
+            if recognized:
+                entry["student_id"], entry["name"] = sid, name
+            else:
+                entry["best_candidate"] = {"student_id": sid, "name": name, "confidence": float(score)}
+            matches.append(entry)
+        return {"image_path": image_path, "num_faces": len(faces),
+                "num_recognized": sum(1 for m in matches if m.get("recognized", False)), "matches": matches,
+                "threshold": self.similarity_threshold, "timestamp": datetime.now().isoformat()}
+
+    # ------------------------------------------------------------------ directory flow
+    def process_capture_directory(self, capture_dir: str, save_results: bool = True) -> Dict:
+        if not os.path.exists(capture_dir):
+            raise ValueError(f"Capture directory not found: {capture_dir}")
+        track_dirs = [os.path.join(capture_dir, d) for d in sorted(os.listdir(capture_dir))
+                      if d.startswith("track_") and os.path.isdir(os.path.join(capture_dir, d))]
+        if not track_dirs:
+            print("No track directories found!")
+            return {"error": "no_tracks"}
+        results = []
+        for td in track_dirs:
+            r = self.match_track(td, top_k=3)
+            if r is None:
+                continue
+            results.append(r)
+            if save_results:
+                with open(os.path.join(td, "recognition_result.json"), "w") as f:
+                    json.dump(r, f, indent=2)
+        recognized = sum(1 for r in results if r["recognized"])
+        summary = self._generate_summary(results, recognized, len(results) - recognized)
+        if save_results:
+            out_dir = os.path.join(capture_dir, f"{self.model_type}_{self.architecture}_results")
+            os.makedirs(out_dir, exist_ok=True)
+            with open(os.path.join(out_dir, "recognition_summary.json"), "w") as f:
+                json.dump(summary, f, indent=2)
+        return summary
+
+    def _generate_summary(self, results: List[Dict], recognized: int, unrecognized: int) -> Dict:
+        appearances = Counter(r["name"] for r in results if r["recognized"])
+        conf = [r["confidence"] for r in results if r["recognized"]]
+        return {
+            "total_tracks": len(results),
+            "recognized": recognized,
+            "unrecognized": unrecognized,
+            "recognition_rate": recognized / len(results) * 100 if results else 0,
+            "avg_confidence": float(np.mean(conf)) if conf else 0.0,
+            "student_appearances": dict(appearances.most_common()),
+            "below_threshold_candidates": [r["best_candidate"] for r in results
+                                           if not r["recognized"] and "best_candidate" in r],
+            "unique_students": len(appearances),
+            "timestamp": datetime.now().isoformat(),
+            "settings": {"similarity_threshold": self.similarity_threshold,
+                         "aggregation_method": self.aggregation_method},
+        }
