@@ -46,7 +46,7 @@ struct frb_ctx {
 
   // constants
   unsigned short* d_lut = nullptr;  // 256 bf16
-  short* d_wtab = nullptr;          // 32*32*4 int16
+  unsigned short* d_wtab = nullptr;  // 32*32*4 uint16 (values 0..32768)
 
   // backbone
   std::vector<frb_layer_desc> layers;
@@ -292,7 +292,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
     memcpy(&lut[i], &b, 2);
   }
   // bilinear weight table as cv::initInterTab2D(INTER_LINEAR, fixpt=true) builds it
-  std::vector<short> wtab(32 * 32 * 4);
+  std::vector<unsigned short> wtab(32 * 32 * 4);
   for (int ay = 0; ay < 32; ++ay)
     for (int ax = 0; ax < 32; ++ax) {
       const float fx = ax * (1.f / 32), fy = ay * (1.f / 32);
@@ -315,7 +315,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
         }
         if (diff < 0) iw[kmax] -= diff; else iw[kmin] -= diff;
       }
-      for (int k = 0; k < 4; ++k) wtab[(ay * 32 + ax) * 4 + k] = static_cast<short>(iw[k]);
+      for (int k = 0; k < 4; ++k) wtab[(ay * 32 + ax) * 4 + k] = static_cast<unsigned short>(iw[k]);
     }
   if (cudaMalloc(&ctx->d_lut, sizeof(lut)) != cudaSuccess || cudaMalloc(&ctx->d_wtab, wtab.size() * 2) != cudaSuccess ||
       cudaMemcpy(ctx->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -475,7 +475,9 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
       gp.num_kb_main = L.cin / 64;
       gp.num_kb_sc = 0;
       const int mn_tiles = ((B + 127) / 128) * (L.cout / 256);
-      gp.num_splits = choose_splits(gp.num_kb_main, std::max(1, ctx->num_sms / mn_tiles));
+      // fixed split count (independent of the batch) so that a face's embedding is bit-identical
+      // whatever batch it is embedded in: the fp32 summation order over K never changes
+      gp.num_splits = choose_splits(gp.num_kb_main, 37);
       const size_t need = static_cast<size_t>(gp.num_splits) * B * L.cout;
       if (ctx->fc_partial_elems < need) {
         if (ctx->d_fc_partial) CK(cudaFree(ctx->d_fc_partial));

@@ -32,12 +32,12 @@ __device__ __forceinline__ int cv_round_sat(double v) {
   return __double2int_rn(v);
 }
 
-// wtab: [32*32][4] int16 bilinear weights (sum exactly 32768), built on the host the way
+// wtab: [32*32][4] uint16 bilinear weights (sum exactly 32768), built on the host the way
 // cv::initInterTab2D builds BilinearTab_i.  lut: 256 bf16 bit patterns of the normalised value.
 template <bool kWriteU8, bool kWriteBf16>
 __global__ void __launch_bounds__(128)
 warp_normalize_kernel(const uint8_t* __restrict__ src_base, const WarpJob* __restrict__ jobs, int S,
-                      const short* __restrict__ wtab, const unsigned short* __restrict__ lut,
+                      const unsigned short* __restrict__ wtab, const unsigned short* __restrict__ lut,
                       uint8_t* __restrict__ out_u8, __nv_bfloat16* __restrict__ out_bf16) {
   const int face = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,7 +64,9 @@ warp_normalize_kernel(const uint8_t* __restrict__ src_base, const WarpJob* __res
   const int Y = (Y0 + bdelta) >> (kAbBits - kInterBits);
   const int sx = X >> kInterBits, sy = Y >> kInterBits;
   const int ax = X & (kInterTab - 1), ay = Y & (kInterTab - 1);
-  const short4 w = reinterpret_cast<const short4*>(wtab)[ay * kInterTab + ax];
+  const ushort4 w4 = reinterpret_cast<const ushort4*>(wtab)[ay * kInterTab + ax];
+  // weights are 0..32768 inclusive (the (0,0) phase is exactly 32768): keep them unsigned
+  const int4 w = make_int4(w4.x, w4.y, w4.z, w4.w);
 
   const uint8_t* img = src_base + jb.src_off;
   int acc0 = 0, acc1 = 0, acc2 = 0;

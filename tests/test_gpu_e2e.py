@@ -32,22 +32,27 @@ def test_config1_match_single_face_loop(tmp_path):
     for i, row in enumerate(G):
         gm.add_student(f"STU{i:04d}", f"Student {i}", row)
     gm.save()
-    thr = 0.5
+    thr = 0.85   # genuine probes score ~1.0, impostors (other noise crops) ~0.6-0.72 with random-init weights
     fm = FaceMatcher(gallery_path=str(tmp_path / "students.pkl"), similarity_threshold=thr, architecture="ir_50",
                      embedder=FaceEmbedder("ir_50", state_dict=sd))
     ref_emb = orc.extract_embeddings_batch(probes)
     eidx, esc = og.search_batch(G, ref_emb, 5)
-    # the oracle's own decision margins must exceed the embedding tolerance, else the case is ill-posed
-    assert (esc[:, 0] - esc[:, 1]).min() > 0.02
-    assert np.abs(esc[:, 0] - thr).min() > 0.02
+    # accept/reject must be well-posed for every probe; top-1 identity for every probe whose oracle margin
+    # (top-1 minus top-2) exceeds the embedding tolerance — random-init nets map unrelated noise crops to
+    # near-equidistant embeddings, so impostors' "identity" is decided by margins of ~1e-3 and is ill-posed.
+    margin = esc[:, 0] - esc[:, 1]
+    well_posed = margin > 0.02
+    assert well_posed[:24].all()
+    assert np.abs(esc[:, 0] - thr).min() > 0.05
     for p, crop in enumerate(probes):
         res = fm.match_single_face(crop, top_k=5)
-        assert [r[0] for r in res][0] == f"STU{eidx[p, 0]:04d}"                     # top-1 identity
+        if well_posed[p]:
+            assert res[0][0] == f"STU{eidx[p, 0]:04d}"                              # top-1 identity
+            assert res[0][1] == f"Student {eidx[p, 0]}"
         assert (res[0][2] >= thr) == (esc[p, 0] >= thr)                             # accept / reject
-        assert abs(res[0][2] - esc[p, 0]) < 5e-3
-        assert isinstance(res[0][2], float) and res[0][1] == f"Student {eidx[p, 0]}"
+        assert abs(res[0][2] - esc[p, 0]) < 5e-3 and isinstance(res[0][2], float)
     batch, accept = fm.match_faces_batch(probes, top_k=5)
-    assert [b[0][0] for b in batch] == [f"STU{i:04d}" for i in eidx[:, 0]]
+    assert [b[0][0] for b, w in zip(batch, well_posed) if w] == [f"STU{i:04d}" for i, w in zip(eidx[:, 0], well_posed) if w]
     assert np.array_equal(accept, esc[:, 0] >= thr)
     assert accept[:24].all() and not accept[24:].any()
     # top-k: identical index lists when matching the SAME embeddings (match parity proper is test_gpu_match)
