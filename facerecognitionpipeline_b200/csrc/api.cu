@@ -15,6 +15,7 @@
 
 #include "../../include/frb200.h"
 #include "gemm_sm100.cuh"
+#include "gemm2_sm100.cuh"
 #include "match_sm100.cuh"
 #include "simple_kernels.cuh"
 
@@ -43,6 +44,7 @@ struct frb_ctx {
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   PFN_cuTensorMapEncodeIm2col_v12000 encode_im2col = nullptr;
   int driver_version = 0;
+  int conv_mode = 2;  // 2 = CTA-pair kernel, 1 = 1-CTA kernel with weight multicast
 
   // constants
   unsigned short* d_lut = nullptr;  // 256 bf16
@@ -166,33 +168,88 @@ int make_tmap_im2col(frb_ctx* ctx, CUtensorMap* m, const void* ptr, int N, int H
   return 0;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int CL>
 int launch_gemm_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& gp,
                   int grid, cudaStream_t st) {
-  auto kern = gemm_sm100_kernel<BN, MODE>;
+  auto kern = gemm_sm100_kernel<BN, MODE, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
     attr_set = true;
   }
-  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(a, a2, b, gp);
-  CK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = GemmSmem<BN>::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, a, a2, b, gp));
   ctx->launches++;
   return 0;
 }
 
-int launch_gemm(frb_ctx* ctx, int block_n, int mode, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
-                const GemmParams& gp, int grid, cudaStream_t st) {
-  if (mode == A_IM2COL) {
-    if (block_n == 64) return launch_gemm_t<64, A_IM2COL>(ctx, a, a2, b, gp, grid, st);
-    if (block_n == 128) return launch_gemm_t<128, A_IM2COL>(ctx, a, a2, b, gp, grid, st);
-    if (block_n == 256) return launch_gemm_t<256, A_IM2COL>(ctx, a, a2, b, gp, grid, st);
-  } else {
-    if (block_n == 64) return launch_gemm_t<64, A_TILED>(ctx, a, a2, b, gp, grid, st);
-    if (block_n == 128) return launch_gemm_t<128, A_TILED>(ctx, a, a2, b, gp, grid, st);
-    if (block_n == 256) return launch_gemm_t<256, A_TILED>(ctx, a, a2, b, gp, grid, st);
+// cluster = CTAs sharing (multicasting) one weight tile; grid must be a multiple of it
+int launch_gemm(frb_ctx* ctx, int block_n, int mode, int cluster, const CUtensorMap& a, const CUtensorMap& a2,
+                const CUtensorMap& b, const GemmParams& gp, int grid, cudaStream_t st) {
+  if (mode == A_IM2COL && cluster == 2) {
+    if (block_n == 64) return launch_gemm_t<64, A_IM2COL, 2>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 128) return launch_gemm_t<128, A_IM2COL, 2>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 256) return launch_gemm_t<256, A_IM2COL, 2>(ctx, a, a2, b, gp, grid, st);
+  } else if (mode == A_IM2COL && cluster == 1) {
+    if (block_n == 64) return launch_gemm_t<64, A_IM2COL, 1>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 128) return launch_gemm_t<128, A_IM2COL, 1>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 256) return launch_gemm_t<256, A_IM2COL, 1>(ctx, a, a2, b, gp, grid, st);
+  } else if (mode == A_TILED && cluster == 1) {
+    if (block_n == 64) return launch_gemm_t<64, A_TILED, 1>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 128) return launch_gemm_t<128, A_TILED, 1>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 256) return launch_gemm_t<256, A_TILED, 1>(ctx, a, a2, b, gp, grid, st);
   }
-  return fail(ctx, "unsupported block_n %d", block_n);
+  return fail(ctx, "unsupported gemm config block_n=%d mode=%d cluster=%d", block_n, mode, cluster);
+}
+
+constexpr int kConvCluster = 2;
+
+template <int BN>
+int launch_gemm2_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& gp,
+                   int grid, cudaStream_t st) {
+  auto kern = gemm2_sm100_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::kTotal));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemm2Threads);
+  cfg.dynamicSmemBytes = Gemm2Smem<BN>::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, a, a2, b, gp));
+  ctx->launches++;
+  return 0;
+}
+
+// Convolution launch: CTA-pair kernel (cta_group::2) by default; FRB_CONV_MODE=1 selects the
+// 1-CTA kernel with 2-way weight multicast (kept for A/B profiling and as the FC/GEMM core).
+int launch_conv(frb_ctx* ctx, int block_n, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
+                const GemmParams& gp, int grid, cudaStream_t st) {
+  if (ctx->conv_mode == 1) return launch_gemm(ctx, block_n, A_IM2COL, kConvCluster, a, a2, b, gp, grid, st);
+  if (block_n == 64) return launch_gemm2_t<64>(ctx, a, a2, b, gp, grid, st);
+  if (block_n == 128) return launch_gemm2_t<128>(ctx, a, a2, b, gp, grid, st);
+  if (block_n == 256) return launch_gemm2_t<256>(ctx, a, a2, b, gp, grid, st);
+  return fail(ctx, "unsupported conv block_n=%d", block_n);
 }
 
 int pick_block_n(int cout) { return cout >= 256 ? 256 : (cout >= 128 ? 128 : 64); }
@@ -238,9 +295,10 @@ int setup_conv(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, c
   }
   const int ktot = (gp->num_kb_main + gp->num_kb_sc) * 64;
   *block_n = pick_block_n(L.cout);
-  if (make_tmap_2d(ctx, tmB, d_w, ktot, L.cout, *block_n)) return 1;
-  const int tiles = ((gp->M + 127) / 128) * (L.cout / *block_n);
-  *grid = std::min(tiles, ctx->num_sms);
+  if (make_tmap_2d(ctx, tmB, d_w, ktot, L.cout, *block_n / kConvCluster)) return 1;
+  const int m_super = ((gp->M + 127) / 128 + kConvCluster - 1) / kConvCluster;
+  const int units = m_super * (L.cout / *block_n);
+  *grid = std::min(units, ctx->num_sms / kConvCluster) * kConvCluster;
   return 0;
 }
 
@@ -274,6 +332,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   }
   ctx->num_sms = prop.multiProcessorCount;
   cudaDriverGetVersion(&ctx->driver_version);
+  if (const char* e = getenv("FRB_CONV_MODE")) ctx->conv_mode = atoi(e);
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -520,9 +579,9 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
       CK(cudaGetLastError());
       ctx->launches++;
     } else if (L.op == FRB_OP_CONV) {
-      if (launch_gemm(ctx, pl.block_n[i], A_IM2COL, pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
+      if (launch_conv(ctx, pl.block_n[i], pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
     } else if (L.op == FRB_OP_FC) {
-      if (launch_gemm(ctx, 256, A_TILED, pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
+      if (launch_gemm(ctx, 256, A_TILED, 1, pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
       const bool flipf = (flags & FRB_EMBED_FLIP) != 0;
       float* emb_dst = d_emb;
       void* bf_dst = d_emb_bf16;
@@ -686,10 +745,26 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
   mp.N = N;
   mp.p_tiles = (P + 127) / 128;
   mp.g_tiles = static_cast<int>((N + kMatchBN - 1) / kMatchBN);
-  int want_slices = std::max(1, (ctx->num_sms * 8 + mp.p_tiles - 1) / mp.p_tiles);
-  want_slices = std::min(want_slices, std::min(mp.g_tiles, kMaxCandPad / kCand));
-  mp.tiles_per_slice = (mp.g_tiles + want_slices - 1) / want_slices;
-  mp.slices = (mp.g_tiles + mp.tiles_per_slice - 1) / mp.tiles_per_slice;
+  // Slices: long enough that the per-row top-k lists settle (few insertions => cheap epilogue), and
+  // p_tiles * slices close to a multiple of the SM count (whole waves).  cost ~ waves * tiles-per-slice.
+  {
+    const int smin = std::max(1, (ctx->num_sms + mp.p_tiles - 1) / mp.p_tiles);
+    const int smax = std::max(1, std::min(std::min(mp.g_tiles, kMaxCandPad / kCand), smin * 8));
+    long best_cost = -1;
+    int best_s = 1;
+    for (int sl = std::min(smin, smax); sl <= smax; ++sl) {
+      const int tps = (mp.g_tiles + sl - 1) / sl;
+      const int real = (mp.g_tiles + tps - 1) / tps;
+      const long waves = (static_cast<long>(mp.p_tiles) * real + ctx->num_sms - 1) / ctx->num_sms;
+      const long cost = waves * (tps + 2);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_s = real;
+      }
+    }
+    mp.tiles_per_slice = (mp.g_tiles + best_s - 1) / best_s;
+    mp.slices = (mp.g_tiles + mp.tiles_per_slice - 1) / mp.tiles_per_slice;
+  }
   if (ctx->match_cap_slices < mp.slices || !ctx->d_cand_score) {
     if (ctx->d_cand_score) CK(cudaFree(ctx->d_cand_score));
     if (ctx->d_cand_idx) CK(cudaFree(ctx->d_cand_idx));
@@ -903,7 +978,7 @@ extern "C" int frb_debug_gemm(frb_ctx* ctx, const void* d_A, const void* d_B, in
   if (make_tmap_2d(ctx, &a, d_A, K, M, 128)) return 1;
   if (make_tmap_2d(ctx, &b, d_B, K, N, bn)) return 1;
   const int tiles = ((M + 127) / 128) * (N / bn) * gp.num_splits;
-  return launch_gemm(ctx, bn, A_TILED, a, a, b, gp, std::min(tiles, ctx->num_sms), static_cast<cudaStream_t>(stream));
+  return launch_gemm(ctx, bn, A_TILED, 1, a, a, b, gp, std::min(tiles, ctx->num_sms), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int frb_debug_conv(frb_ctx* ctx, const frb_layer_desc* L, int B, const void* d_in, const void* d_sc,
@@ -940,7 +1015,7 @@ extern "C" int frb_debug_conv(frb_ctx* ctx, const frb_layer_desc* L, int B, cons
   frb_layer_desc LL = *L;
   if (!d_sc) { LL.sc_buf = -1; LL.sc_cin = 0; }
   if (setup_conv(ctx, LL, B, d_in, d_sc, d_res, d_w, d_bias, d_prelu, d_out, &a, &a2, &b, &gp, &bn, &grid)) return 1;
-  return launch_gemm(ctx, bn, A_IM2COL, a, a2, b, gp, grid, st);
+  return launch_conv(ctx, bn, a, a2, b, gp, grid, st);
 }
 
 namespace {

@@ -1,0 +1,342 @@
+// gemm2_sm100.cuh — the implicit-GEMM convolution on CTA PAIRS (tcgen05 cta_group::2).
+//
+// Why: profiles/r01b show the 1-CTA kernel (gemm_sm100.cuh) bound by shared-memory bandwidth, not
+// by L2 or the tensor pipe: per 128-cycle MMA (128x256x16) an SM reads 4 KB of A + 8 KB of B from
+// shared memory while TMA writes the next stage into it.  A CTA pair computes a 256 x N tile with
+// ONE instruction stream: each SM stages only its own 128 A rows and HALF of the weight tile
+// (N/2 rows), the tensor cores exchange the B halves across the pair.  That halves B's L2->SM
+// traffic, its shared-memory footprint (deeper pipeline: 6-9 stages instead of 4-8) and the
+// shared-memory read pressure per MMA cycle.
+//
+// Cluster = (2,1,1).  CTA rank 0 ("leader") issues all tcgen05.mma; both CTAs run a TMA producer
+// (own A rows + own B half, completing on the LEADER's full barrier) and four epilogue warps
+// (own 128 accumulator rows, in their own TMEM).
+#pragma once
+#include "gemm_sm100.cuh"
+
+namespace frb {
+
+// ---- cluster-scope PTX used only here
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_smem_addr, uint32_t target_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(target_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-SM TMA forms: `bar_cluster_addr` is a shared::cluster address (the leader's barrier).
+constexpr uint64_t kTmaMemDescDefault = 0x1000000000000000ull;
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
+      "l"(kTmaMemDescDefault)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c,
+                                                    int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h),
+      "r"(n), "h"(off_w), "h"(off_h), "l"(kTmaMemDescDefault)
+      : "memory");
+}
+__device__ __forceinline__ void tmem2_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem2_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_pair(uint64_t* bar) {  // arrive on `bar` in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+constexpr int kGemm2Threads = 320;  // producer warp + MMA warp + 8 epilogue warps
+
+template <int BLOCK_N>
+struct Gemm2Smem {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;            // own 128 A rows: 16 KB
+  static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;      // own half of the weight tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 6 : (BLOCK_N == 128 ? 8 : 9);
+  static constexpr int kAccStages = 2;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kEpiBytes = 10 * BLOCK_N * 4;  // bias table [<=9][BLOCK_N] + PReLU [BLOCK_N], fp32
+  static constexpr int kTotal = kStages * kStageBytes + 512 + kEpiBytes + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemm2Threads, 1)
+gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                   const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using S = Gemm2Smem<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S::kStages * S::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* full_bar = bars;                        // used in the leader only
+  uint64_t* empty_bar = bars + S::kStages;          // per CTA, signalled by the leader's commit
+  uint64_t* tmem_full_bar = bars + 2 * S::kStages;  // per CTA, signalled by the leader's commit
+  uint64_t* tmem_empty_bar = tmem_full_bar + S::kAccStages;  // leader only: 8 epilogue warps arrive
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + S::kAccStages);
+  float* s_bias = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + 512);  // [cases][BLOCK_N]
+  float* s_prelu = s_bias + 9 * BLOCK_N;                                               // [BLOCK_N]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(cluster_ctarank());
+  const bool leader = (crank == 0);
+
+  const int m_pairs = ((p.M + kBlockM - 1) / kBlockM + 1) / 2;  // 256-row super tiles
+  const int n_tiles = p.N / BLOCK_N;
+  const int num_kb = p.num_kb_main + p.num_kb_sc;
+  const int total_tiles = m_pairs * n_tiles;
+  const int first_tile = blockIdx.x >> 1;
+  const int tile_step = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (p.num_kb_sc > 0) prefetch_tmap(&tmA2);
+    for (int i = 0; i < S::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < S::kAccStages; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 16);  // 8 epilogue warps in each of the 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem2_alloc(tmem_ptr_smem, S::kTmemCols);
+    tmem2_relinquish();
+  }
+  // Per-layer epilogue constants live in shared memory (they were a ~400-cycle global-load stall per
+  // 32-column chunk).  With one N tile they are loaded once; Cout = 512 reloads per tile below.
+  if (p.N == BLOCK_N) {
+    for (int i = threadIdx.x; i < p.bias_cases * BLOCK_N; i += kGemm2Threads) s_bias[i] = p.bias[i];
+    if (p.prelu != nullptr)
+      for (int i = threadIdx.x; i < BLOCK_N; i += kGemm2Threads) s_prelu[i] = p.prelu[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int n_tile = tile % n_tiles;
+        const int m_tile = (tile / n_tiles) * 2 + crank;
+        const int m0 = (m_tile * kBlockM < p.M) ? m_tile * kBlockM : 0;  // padding tile: re-read tile 0, stores masked
+        const int pq = p.P * p.Q;
+        const int img = m0 / pq;
+        const int rem = m0 - img * pq;
+        const int pp = rem / p.Q;
+        const int qq = rem - pp * p.Q;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+          void* sa = smem_a + stage * S::kABytes;
+          void* sb = smem_b + stage * S::kBBytes;
+          if (kb < p.num_kb_main) {
+            const int tap = kb / p.cin_chunks;
+            const int cc = kb - tap * p.cin_chunks;
+            const int r = (p.pad ? tap / 3 : 0), s = (p.pad ? tap - 3 * (tap / 3) : 0);
+            tma2_load_im2col_4d(&tmA, full_leader, sa, cc * kBlockK, qq * p.stride - p.pad, pp * p.stride - p.pad, img,
+                                static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+          } else {
+            const int cc = kb - p.num_kb_main;
+            tma2_load_im2col_4d(&tmA2, full_leader, sa, cc * kBlockK, qq * p.sc_stride, pp * p.sc_stride, img, 0, 0);
+          }
+          tma2_load_2d(&tmB, full_leader, sb, kb * kBlockK, n_tile * BLOCK_N + crank * (BLOCK_N / 2));
+          if (++stage == S::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * S::kABytes));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * S::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma2_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma2_commit_pair(&empty_bar[stage]);   // frees this stage in both CTAs
+          if (++stage == S::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma2_commit_pair(&tmem_full_bar[acc]);   // accumulators ready in both CTAs
+        if (++acc == S::kAccStages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..9 (both CTAs, own 128 rows) =====================
+    // warp w reads TMEM lane quadrant (w & 3); the two warps of a quadrant take alternate 32-column chunks
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int epi_tid = threadIdx.x - 64;  // 0..255
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int n_tile = tile % n_tiles;
+      const int m_tile = (tile / n_tiles) * 2 + crank;
+      const int row = quad * 32 + lane;
+      const int m = m_tile * kBlockM + row;
+      const bool valid = m < p.M;
+      const int n0 = n_tile * BLOCK_N;
+      int bias_case = 0;
+      size_t res_off = 0;
+      if (valid) {
+        const int pq = p.P * p.Q;
+        const int img = m / pq;
+        const int rem = m - img * pq;
+        const int pp = rem / p.Q;
+        const int qq = rem - pp * p.Q;
+        if (p.bias_cases == 9) {
+          const int rc = (pp == 0) ? 0 : ((pp == p.P - 1) ? 2 : 1);
+          const int cc = (qq == 0) ? 0 : ((qq == p.Q - 1) ? 2 : 1);
+          bias_case = rc * 3 + cc;
+        }
+        if (p.residual != nullptr)
+          res_off = ((static_cast<size_t>(img) * p.RH + static_cast<size_t>(pp) * p.res_stride) * p.RW +
+                     static_cast<size_t>(qq) * p.res_stride) * p.N;
+      }
+      if (p.N != BLOCK_N) {  // several N tiles (Cout = 512): refresh the constants of this tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
+        for (int i = epi_tid; i < p.bias_cases * BLOCK_N; i += 256)
+          s_bias[i] = p.bias[(i / BLOCK_N) * p.N + n0 + (i % BLOCK_N)];
+        if (p.prelu != nullptr)
+          for (int i = epi_tid; i < BLOCK_N; i += 256) s_prelu[i] = p.prelu[n0 + i];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      const float* bias_row = s_bias + bias_case * BLOCK_N;
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = half; c < BLOCK_N / 32; c += 2) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        uint4 rs[4];
+        if (p.residual != nullptr && valid) {  // residual loads fly while the TMEM load completes
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + res_off + n0 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rs[j] = __ldg(rp + j);
+        }
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+          const float4* bp = reinterpret_cast<const float4*>(bias_row + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = bp[j];
+            v[4 * j] = __uint_as_float(r[4 * j]) + b.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+          }
+          if (p.prelu != nullptr) {
+            const float4* s4 = reinterpret_cast<const float4*>(s_prelu + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 sl = s4[j];
+              v[4 * j] = v[4 * j] > 0.f ? v[4 * j] : v[4 * j] * sl.x;
+              v[4 * j + 1] = v[4 * j + 1] > 0.f ? v[4 * j + 1] : v[4 * j + 1] * sl.y;
+              v[4 * j + 2] = v[4 * j + 2] > 0.f ? v[4 * j + 2] : v[4 * j + 2] * sl.z;
+              v[4 * j + 3] = v[4 * j + 3] > 0.f ? v[4 * j + 3] : v[4 * j + 3] * sl.w;
+            }
+          }
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w[4] = {rs[j].x, rs[j].y, rs[j].z, rs[j].w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                v[8 * j + 2 * t] += __uint_as_float(w[t] << 16);
+                v[8 * j + 2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
+              }
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.N + n0 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            dst[j] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      if (++acc == S::kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem2_dealloc(tmem_base, S::kTmemCols);
+  }
+}
+
+}  // namespace frb

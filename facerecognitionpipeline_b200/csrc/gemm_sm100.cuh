@@ -56,7 +56,10 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
 };
 
-template <int BLOCK_N, int A_MODE>
+// CLUSTER > 1: the CTAs of a cluster work on CLUSTER consecutive M tiles of the same N tile and
+// share the weight tile: each CTA fetches 1/CLUSTER of it and TMA-multicasts it to all of them,
+// which divides the L2->SM weight traffic (the measured bound of these convs) by CLUSTER.
+template <int BLOCK_N, int A_MODE, int CLUSTER>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -77,11 +80,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  // work units ("tiles") are enumerated per cluster; CTA `crank` of a cluster takes M tile
+  // m_super * CLUSTER + crank (tiles past the end are all-zero loads with masked stores)
+  const int m_tiles = ((p.M + kBlockM - 1) / kBlockM + CLUSTER - 1) / CLUSTER;  // M super-tiles
   const int n_tiles = p.N / BLOCK_N;
   const int num_kb = p.num_kb_main + p.num_kb_sc;
   const int kb_per_split = (num_kb + p.num_splits - 1) / p.num_splits;
   const int total_tiles = m_tiles * n_tiles * p.num_splits;
+  const int crank = (CLUSTER > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_tile = blockIdx.x / CLUSTER;
+  const int tile_step = gridDim.x / CLUSTER;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CLUSTER) - 1);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -89,7 +98,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.num_kb_sc > 0) prefetch_tmap(&tmA2);
     for (int i = 0; i < S::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CLUSTER);  // one tcgen05.commit arrive from every CTA of the cluster
     }
     for (int i = 0; i < S::kAccStages; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -103,6 +112,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -111,12 +121,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int split = tile % p.num_splits;
         const int mn = tile / p.num_splits;
         const int n_tile = mn % n_tiles;
-        const int m_tile = mn / n_tiles;
-        const int m0 = m_tile * kBlockM;
+        const int m_tile = (mn / n_tiles) * CLUSTER + crank;
+        // a padding tile past the end (odd tile count in a cluster) re-reads tile 0; its stores are masked
+        const int m0 = (m_tile * kBlockM < p.M) ? m_tile * kBlockM : 0;
         int img = 0, pp = 0, qq = 0;
         if (A_MODE == A_IM2COL) {
           const int pq = p.P * p.Q;
@@ -148,7 +159,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           } else {
             tma_load_2d(&tmA, &full_bar[stage], sa, kb * kBlockK, m0);
           }
-          tma_load_2d(&tmB, &full_bar[stage], sb, kb * kBlockK, n_tile * BLOCK_N);
+          if (CLUSTER > 1) {
+            constexpr int kRows = BLOCK_N / CLUSTER;
+            tma_load_2d_mcast(&tmB, &full_bar[stage], static_cast<uint8_t*>(sb) + crank * kRows * 128,
+                              kb * kBlockK, n_tile * BLOCK_N + crank * kRows, kMask);
+          } else {
+            tma_load_2d(&tmB, &full_bar[stage], sb, kb * kBlockK, n_tile * BLOCK_N);
+          }
           if (++stage == S::kStages) {
             stage = 0;
             phase ^= 1;
@@ -164,7 +181,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int split = tile % p.num_splits;
         const int kb_begin = split * kb_per_split;
         const int kb_end = min(num_kb, kb_begin + kb_per_split);
@@ -181,7 +198,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle row (>>4 => +2)
             umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (in every CTA the slot is multicast into)
+          if (CLUSTER > 1) umma_commit_mcast(&empty_bar[stage], kMask);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == S::kStages) {
             stage = 0;
             phase ^= 1;
@@ -199,11 +218,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int split = tile % p.num_splits;
       const int mn = tile / p.num_splits;
       const int n_tile = mn % n_tiles;
-      const int m_tile = mn / n_tiles;
+      const int m_tile = (mn / n_tiles) * CLUSTER + crank;
       const int row = quad * 32 + lane;
       const int m = m_tile * kBlockM + row;
       const bool valid = m < p.M;
@@ -308,6 +327,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();  // no CTA may exit while a peer can still signal its barriers
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();

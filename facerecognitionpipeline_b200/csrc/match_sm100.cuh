@@ -197,9 +197,14 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
           tmem_ld_wait();
           if (c * 32 >= ncols) continue;
           float v[32];
+          if (ncols == kMatchBN) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = (c * 32 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          } else {  // last gallery tile: columns past N are TMA zero fill, not scores
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = (c * 32 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY;
+          }
           float m = v[0];
 #pragma unroll
           for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
