@@ -72,6 +72,8 @@ SIGNATURES = {
     "frb_embed_match_host": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "frb_debug_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "frb_debug_conv": (_i, [_vp, C.POINTER(LayerDesc), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "frb_debug_shift_mma": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "frb_debug_mma_rate": (_i, [_vp, _i, _i, _i, _vp]),
     "frb_debug_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 

@@ -16,6 +16,7 @@
 #include "../../include/frb200.h"
 #include "gemm_sm100.cuh"
 #include "gemm2_sm100.cuh"
+#include "conv_slab_sm100.cuh"
 #include "match_sm100.cuh"
 #include "simple_kernels.cuh"
 
@@ -31,6 +32,9 @@ struct Plan {  // per-batch-size launch plan of the backbone
   std::vector<CUtensorMap> tmA, tmA2, tmB;
   std::vector<GemmParams> gp;
   std::vector<int> block_n, grid;
+  std::vector<int> use_slab;       // 1 = conv_slab_sm100_kernel (3x3 stride-1, W in {28,56,112})
+  std::vector<SlabParams> sp;
+  std::vector<int> slab_smem;
 };
 
 }  // namespace
@@ -45,6 +49,7 @@ struct frb_ctx {
   PFN_cuTensorMapEncodeIm2col_v12000 encode_im2col = nullptr;
   int driver_version = 0;
   int conv_mode = 2;  // 2 = CTA-pair kernel, 1 = 1-CTA kernel with weight multicast
+  int use_slab = 1;   // activation-slab kernel for eligible 3x3 stride-1 layers (FRB_SLAB=0 disables)
 
   // constants
   unsigned short* d_lut = nullptr;  // 256 bf16
@@ -252,6 +257,107 @@ int launch_conv(frb_ctx* ctx, int block_n, const CUtensorMap& a, const CUtensorM
   return fail(ctx, "unsupported conv block_n=%d", block_n);
 }
 
+// NHWC bf16 activation [N][H][W][C] as a tiled 4-D tensor; box = 64 channels x box_w x box_h x 1 image.
+int make_tmap_4d_tiled(frb_ctx* ctx, CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int box_w, int box_h) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = ctx->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, "cuTensorMapEncodeTiled(4d) failed (%d)", (int)r);
+  small_tensor_fixup(ctx, m, (size_t)N * H * W * C * 2);
+  return 0;
+}
+
+int slab_rows(int w) { return w == 112 ? 1 : (w == 56 ? 2 : (w == 28 ? 4 : 0)); }
+
+bool slab_eligible(const frb_ctx* ctx, const frb_layer_desc& L, bool has_sc) {
+  if (ctx->conv_mode != 2 || !ctx->use_slab) return false;
+  if (L.ksize != 3 || L.stride != 1 || L.pad != 1 || has_sc) return false;
+  if (L.hin != L.win || slab_rows(L.win) == 0 || L.hin % slab_rows(L.win)) return false;
+  if (L.cin % 64 || L.cin > 128 || (L.cout != 64 && L.cout != 128 && L.cout != 256)) return false;
+  if (L.res_buf >= 0 && (L.res_stride != 1 || L.res_h != L.hin || L.res_w != L.win)) return false;
+  return true;
+}
+
+int setup_slab(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, const void* d_res, const void* d_w,
+               const float* d_bias, const float* d_prelu, void* d_out, CUtensorMap* tmX, CUtensorMap* tmB,
+               SlabParams* sp, int* smem_bytes, int* grid) {
+  const int W = L.win, R = slab_rows(W);
+  memset(sp, 0, sizeof(*sp));
+  sp->B = B; sp->H = L.hin; sp->W = W; sp->R = R;
+  sp->cin_chunks = L.cin / 64;
+  sp->N = L.cout;
+  sp->num_kb = 9 * sp->cin_chunks;
+  sp->box_bytes = 128 * (W + 2) * (R + 2);
+  const int need = (128 + 2 * (W + 2) + 2) * 128;
+  sp->slab_bytes = std::max((need + 1023) / 1024 * 1024, (sp->box_bytes + 1023) / 1024 * 1024);
+  const int b_bytes = (L.cout / 2) * 128;
+  const int misc = 1024 + 10 * L.cout * 4 + 1024;
+  const int total = 226 * 1024;
+  const int buf_bytes = sp->cin_chunks * sp->slab_bytes;
+  // Depth first: a tile is only 0.6-2.4 us of MMA work, so several slabs must be in flight to hide the
+  // ~2 us load latency.  Weights stay resident when they still fit, else they stream through a ring.
+  int nbuf, st;
+  if (sp->num_kb * b_bytes + 3 * buf_bytes + misc <= total) {
+    st = sp->num_kb;  // resident
+    nbuf = std::min(kSlabMaxBuf, (total - misc - st * b_bytes) / buf_bytes);
+  } else {
+    nbuf = 3;
+    st = std::min(kSlabMaxBStages, (total - misc - nbuf * buf_bytes) / b_bytes);
+    if (st >= sp->num_kb) st = sp->num_kb;
+  }
+  if (st < 3 || nbuf < 2) return fail(ctx, "slab conv: not enough shared memory (stages %d, buffers %d)", st, nbuf);
+  sp->b_stages = st;
+  sp->nbuf = nbuf;
+  *smem_bytes = nbuf * buf_bytes + st * b_bytes + misc;
+  sp->bias = d_bias; sp->bias_cases = L.bias_cases;
+  sp->prelu = L.has_prelu ? d_prelu : nullptr;
+  sp->residual = reinterpret_cast<const __nv_bfloat16*>(d_res);
+  sp->out = reinterpret_cast<__nv_bfloat16*>(d_out);
+  if (make_tmap_4d_tiled(ctx, tmX, d_in, B, L.hin, W, L.cin, W + 2, R + 2)) return 1;
+  if (make_tmap_2d(ctx, tmB, d_w, sp->num_kb * 64, L.cout, L.cout / 2)) return 1;
+  const int pairs = (B * (L.hin / R) + 1) / 2;
+  *grid = std::min(pairs, ctx->num_sms / 2) * 2;
+  return 0;
+}
+
+template <int BN>
+int launch_slab_t(frb_ctx* ctx, const CUtensorMap& x, const CUtensorMap& b, const SlabParams& sp, int smem_bytes, int grid,
+                  cudaStream_t st) {
+  auto kern = conv_slab_sm100_kernel<BN>;
+  static int attr_bytes = 0;
+  if (attr_bytes < smem_bytes) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_bytes = 227 * 1024;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemm2Threads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, x, b, sp));
+  ctx->launches++;
+  return 0;
+}
+
+int launch_slab(frb_ctx* ctx, const CUtensorMap& x, const CUtensorMap& b, const SlabParams& sp, int smem_bytes, int grid,
+                cudaStream_t st) {
+  if (sp.N == 64) return launch_slab_t<64>(ctx, x, b, sp, smem_bytes, grid, st);
+  if (sp.N == 128) return launch_slab_t<128>(ctx, x, b, sp, smem_bytes, grid, st);
+  if (sp.N == 256) return launch_slab_t<256>(ctx, x, b, sp, smem_bytes, grid, st);
+  return fail(ctx, "slab conv: unsupported Cout %d", sp.N);
+}
+
 int pick_block_n(int cout) { return cout >= 256 ? 256 : (cout >= 128 ? 128 : 64); }
 
 int out_dim(int in, int ksize, int stride, int pad) { return (in + 2 * pad - ksize) / stride + 1; }
@@ -333,6 +439,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   cudaDriverGetVersion(&ctx->driver_version);
   if (const char* e = getenv("FRB_CONV_MODE")) ctx->conv_mode = atoi(e);
+  if (const char* e = getenv("FRB_SLAB")) ctx->use_slab = atoi(e);
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -514,6 +621,7 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
   Plan& pl = ctx->plan;
   pl.B = B;
   pl.tmA.resize(nl); pl.tmA2.resize(nl); pl.tmB.resize(nl); pl.gp.resize(nl); pl.block_n.assign(nl, 0); pl.grid.assign(nl, 0);
+  pl.use_slab.assign(nl, 0); pl.sp.resize(nl); pl.slab_smem.assign(nl, 0);
   for (size_t i = 0; i < nl; ++i) {
     const frb_layer_desc& L = ctx->layers[i];
     const void* in = L.in_buf < 0 ? d_in : ctx->d_bufs[L.in_buf];
@@ -521,6 +629,16 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
     if (L.op == FRB_OP_CONV) {
       const void* sc = L.sc_buf >= 0 ? ctx->d_bufs[L.sc_buf] : nullptr;
       const void* res = L.res_buf >= 0 ? ctx->d_bufs[L.res_buf] : nullptr;
+      if (slab_eligible(ctx, L, sc != nullptr)) {
+        pl.use_slab[i] = 1;
+        if (setup_slab(ctx, L, B, in, res, blob + L.w_off, reinterpret_cast<const float*>(blob + L.bias_off),
+                       reinterpret_cast<const float*>(blob + L.prelu_off), ctx->d_bufs[L.out_buf], &pl.tmA[i], &pl.tmB[i],
+                       &pl.sp[i], &pl.slab_smem[i], &pl.grid[i]))
+          return 1;
+        memset(&pl.gp[i], 0, sizeof(GemmParams));
+        pl.gp[i].M = 1;  // plan marker: non-empty
+        continue;
+      }
       if (setup_conv(ctx, L, B, in, sc, res, blob + L.w_off, reinterpret_cast<const float*>(blob + L.bias_off),
                      reinterpret_cast<const float*>(blob + L.prelu_off), ctx->d_bufs[L.out_buf], &pl.tmA[i],
                      &pl.tmA2[i], &pl.tmB[i], &pl.gp[i], &pl.block_n[i], &pl.grid[i]))
@@ -579,7 +697,9 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
       CK(cudaGetLastError());
       ctx->launches++;
     } else if (L.op == FRB_OP_CONV) {
-      if (launch_conv(ctx, pl.block_n[i], pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
+      if (pl.use_slab[i]) {
+        if (launch_slab(ctx, pl.tmA[i], pl.tmB[i], pl.sp[i], pl.slab_smem[i], pl.grid[i], st)) return 1;
+      } else if (launch_conv(ctx, pl.block_n[i], pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
     } else if (L.op == FRB_OP_FC) {
       if (launch_gemm(ctx, 256, A_TILED, 1, pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
       const bool flipf = (flags & FRB_EMBED_FLIP) != 0;
@@ -1014,6 +1134,13 @@ extern "C" int frb_debug_conv(frb_ctx* ctx, const frb_layer_desc* L, int B, cons
   int bn, grid;
   frb_layer_desc LL = *L;
   if (!d_sc) { LL.sc_buf = -1; LL.sc_cin = 0; }
+  if (!d_res) LL.res_buf = -1;
+  if (slab_eligible(ctx, LL, d_sc != nullptr)) {
+    SlabParams sp;
+    int smem_bytes;
+    if (setup_slab(ctx, LL, B, d_in, d_res, d_w, d_bias, d_prelu, d_out, &a, &b, &sp, &smem_bytes, &grid)) return 1;
+    return launch_slab(ctx, a, b, sp, smem_bytes, grid, st);
+  }
   if (setup_conv(ctx, LL, B, d_in, d_sc, d_res, d_w, d_bias, d_prelu, d_out, &a, &a2, &b, &gp, &bn, &grid)) return 1;
   return launch_conv(ctx, bn, a, a2, b, gp, grid, st);
 }
@@ -1056,5 +1183,173 @@ extern "C" int frb_debug_im2col(frb_ctx* ctx, const void* d_in, int B, int H, in
       tm, c0, qq * stride - pad, pp * stride - pad, img, tap_s, tap_r, reinterpret_cast<uint4*>(d_out_16k));
   CK(cudaGetLastError());
   ctx->launches++;
+  return 0;
+}
+
+// ---- probe: how does tcgen05.mma read a 128B-swizzled K-major A operand whose start is NOT 1024-byte
+// aligned (row offset j0 into a TMA-written slab)?  mode 0: plain descriptor; mode 1: base_offset field set
+// to address bits [7,10).  D[128][64] = slab[j0 : j0+128][0:64] * B[64][64]^T
+namespace {
+__global__ void shift_mma_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_constant__ CUtensorMap tmB,
+                                 int j0, int mode, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;            // 256 rows x 128 B
+  uint8_t* sB = smem + 32768;    // 64 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 32768 + 8192);
+  uint64_t* done = bar + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tptr, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, 32768 + 8192);
+    tma_load_2d(&tmSlab, bar, sA, 0, 0);
+    tma_load_2d(&tmSlab, bar, sA + 16384, 0, 128);
+    tma_load_2d(&tmB, bar, sB, 0, 0);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const uint32_t a_addr = smem_u32(sA) + j0 * 128;
+    uint64_t adesc = umma_desc_sw128(a_addr);
+    if (mode == 1) adesc |= static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
+    const uint64_t bdesc = umma_desc_sw128(smem_u32(sB));
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+    for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
+    umma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  {
+    const int row = warp * 32 + lane;
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) out[row * 64 + c * 32 + j] = __uint_as_float(r[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, 64);
+  }
+}
+}  // namespace
+
+extern "C" int frb_debug_shift_mma(frb_ctx* ctx, const void* d_slab_256x64, const void* d_B_64x64, int j0, int mode,
+                                   float* d_out_128x64, void* stream) {
+  if (!ctx) return 1;
+  if (j0 < 0 || j0 > 128) return fail(ctx, "j0 out of range");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CUtensorMap ta, tb;
+  if (make_tmap_2d(ctx, &ta, d_slab_256x64, 64, 256, 128)) return 1;
+  if (make_tmap_2d(ctx, &tb, d_B_64x64, 64, 64, 64)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(shift_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8192 + 64 + 1024));
+    attr_set = true;
+  }
+  shift_mma_kernel<<<1, 128, 32768 + 8192 + 64 + 1024, static_cast<cudaStream_t>(stream)>>>(ta, tb, j0, mode, d_out_128x64);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+// ---- probe: issue rate of tcgen05.mma (cta_group::1, operands resident in smem, one accumulator):
+// cycles per instruction as seen by the issuing thread (issue) and until the commit lands (complete).
+namespace {
+template <int N>
+__global__ void mma_rate_kernel(int iters, int mode, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;            // 128 x 128 B
+  uint8_t* sB = smem + 16384;    // 256 x 128 B
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 16384 + 32768);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tptr, 256);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tptr, 0);
+  if (warp == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+    const uint64_t adesc = umma_desc_sw128(smem_u32(sA));
+    const uint64_t bdesc = umma_desc_sw128(smem_u32(sB));
+    long long t0 = clock64();
+    if (mode == 0) {            // whole loop inside one elected lane
+      if (elect_one()) {
+        for (int i = 0; i < iters; ++i) umma_bf16_ss(tmem, adesc + 2 * (i & 3), bdesc + 2 * (i & 3), idesc, i > 0 ? 1u : 0u);
+        umma_commit(done);
+      }
+    } else {                     // converged loop, elect per issue (CUTLASS style)
+      for (int i = 0; i < iters; ++i) {
+        const uint64_t a = adesc + 2 * (i & 3), b = bdesc + 2 * (i & 3);
+        if (elect_one()) umma_bf16_ss(tmem, a, b, idesc, i > 0 ? 1u : 0u);
+      }
+      if (elect_one()) umma_commit(done);
+    }
+    __syncwarp();
+    long long t1 = clock64();
+    mbar_wait(done, 0);
+    long long t2 = clock64();
+    if (threadIdx.x == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+}  // namespace
+
+extern "C" int frb_debug_mma_rate(frb_ctx* ctx, int N, int iters, int mode, long long* h_out2) {
+  if (!ctx) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  long long* d = nullptr;
+  CK(cudaMalloc(&d, 16));
+  const int smem = 16384 + 32768 + 64 + 1024;
+  if (N == 64) {
+    CK(cudaFuncSetAttribute(mma_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma_rate_kernel<64><<<1, 64, smem>>>(iters, mode, d);
+  } else if (N == 128) {
+    CK(cudaFuncSetAttribute(mma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma_rate_kernel<128><<<1, 64, smem>>>(iters, mode, d);
+  } else {
+    CK(cudaFuncSetAttribute(mma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma_rate_kernel<256><<<1, 64, smem>>>(iters, mode, d);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(h_out2, d, 16, cudaMemcpyDeviceToHost));
+  CK(cudaFree(d));
   return 0;
 }

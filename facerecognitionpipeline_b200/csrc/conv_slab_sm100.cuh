@@ -1,0 +1,309 @@
+// conv_slab_sm100.cuh — 3x3 stride-1 convolution with ACTIVATION SLAB REUSE on CTA pairs.
+//
+// profiles/r01b + tools/microbench_gemm.py: the im2col implicit GEMM re-fetches every input pixel
+// nine times (once per filter tap) and, for Cout <= 128, is bound by L2->SM operand ingest
+// (~42 B/clk/SM), not by the tensor pipe: 377 TF (Cout 64) / 718 TF (Cout 128).
+//
+// Here a CTA loads, ONCE per tile, the input rows it needs including the 1-pixel halo
+// ("slab": (R+2) x (W+2) pixels x 64 channels, one tiled-TMA box whose out-of-bounds part is the
+// convolution's zero padding) and the nine taps read it through nine shifted UMMA descriptors:
+// for 128B-swizzled K-major operands tcgen05.mma derives the swizzle from the shared-memory address
+// (tools/probe_shift.py: any row offset works with a plain descriptor), so tap (r,s) is simply the
+// slab base + (r*(W+2)+s) rows.  Accumulator row i is the padded-row-major position i of the tile:
+// positions with (i mod (W+2)) >= W or i >= R*(W+2) are halo columns / unused rows and are
+// skipped by the epilogue (12.5 % of the MMA rows at W = 112/56/28 with R = 1/2/4).
+// Activation ingest drops ~8x; weights stay resident in shared memory when they fit (Cin = 64).
+//
+// CTA pair (cluster 2, tcgen05 cta_group::2) as in gemm2_sm100.cuh: the leader issues the MMAs
+// (M = 256 = two tiles), each CTA owns one tile's slab, half of the weight tile and 128 TMEM lanes.
+#pragma once
+#include "gemm2_sm100.cuh"
+
+namespace frb {
+
+struct SlabParams {
+  int B, H, W, R;        // images, spatial size (H == W of the layer), rows per tile
+  int cin_chunks;        // Cin / 64 (1 or 2)
+  int N;                 // Cout
+  int num_kb;            // 9 * cin_chunks
+  int b_stages;          // weight ring depth; == num_kb => weights resident
+  int nbuf;              // slab buffers in flight (2..6): tiles are short, so depth hides the load latency
+  int slab_bytes;        // per (buffer, chunk), multiple of 1024
+  int box_bytes;         // bytes one slab TMA box delivers
+  const float* bias;     // [bias_cases][N]
+  int bias_cases;
+  const float* prelu;    // [N] or nullptr
+  const __nv_bfloat16* residual;  // identity shortcut (same shape as out) or nullptr
+  __nv_bfloat16* out;    // [B][H][W][N]
+};
+
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "l"(kTmaMemDescDefault)
+      : "memory");
+}
+
+constexpr int kSlabMaxBStages = 18;
+constexpr int kSlabMaxBuf = 6;
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemm2Threads, 1)
+conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
+                       const SlabParams p) {
+  constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;
+  constexpr int kAcc = (512 / BLOCK_N) < 4 ? (512 / BLOCK_N) : 4;  // TMEM accumulator stages
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int slab_buf_bytes = p.cin_chunks * p.slab_bytes;
+  uint8_t* smem_slab = smem;                                  // [nbuf][chunks][slab_bytes]
+  uint8_t* smem_b = smem + p.nbuf * slab_buf_bytes;           // [b_stages][kBBytes]
+  uint8_t* tail = smem_b + p.b_stages * kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* slab_full = bars;                             // [6]  leader only
+  uint64_t* slab_empty = bars + kSlabMaxBuf;              // [6]  per CTA
+  uint64_t* b_full = bars + 2 * kSlabMaxBuf;              // [18] leader only
+  uint64_t* b_empty = b_full + kSlabMaxBStages;           // [18] per CTA
+  uint64_t* tmem_full_bar = b_empty + kSlabMaxBStages;    // [4] per CTA
+  uint64_t* tmem_empty_bar = tmem_full_bar + 4;           // [4] leader only, 16 arrivals
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 4);
+  float* s_bias = reinterpret_cast<float*>(tail + 1024);      // [9][BLOCK_N]
+  float* s_prelu = s_bias + 9 * BLOCK_N;
+
+  // shuffle-broadcast makes the warp index provably warp-uniform for ptxas (uniform branches / registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(cluster_ctarank());
+  const bool leader = (crank == 0);
+  const int Wp = p.W + 2;
+  const int tiles_per_img = p.H / p.R;
+  const int num_tiles = p.B * tiles_per_img;
+  const int total_pairs = (num_tiles + 1) / 2;
+  const int first_pair = blockIdx.x >> 1;
+  const int pair_step = gridDim.x >> 1;
+  const bool resident = (p.b_stages == p.num_kb);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < kSlabMaxBuf; ++i) {
+      mbar_init(&slab_full[i], 1);
+      mbar_init(&slab_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 16);
+    }
+    for (int i = 0; i < kSlabMaxBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem2_alloc(tmem_ptr_smem, kAcc * BLOCK_N);
+    tmem2_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.bias_cases * BLOCK_N; i += kGemm2Threads) s_bias[i] = p.bias[i];
+  if (p.prelu != nullptr)
+    for (int i = threadIdx.x; i < BLOCK_N; i += kGemm2Threads) s_prelu[i] = p.prelu[i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    // Slabs are issued as far ahead as buffers allow (up to nbuf tiles), interleaved with the weight
+    // K blocks of the current tile, so the slab depth is not throttled by the weight ring.
+    if (lane == 0) {
+      const int n_iters = (total_pairs - first_pair + pair_step - 1) / pair_step;
+      int next = 0;  // next iteration whose slab has not been issued yet
+      auto issue_slab = [&](int j) {
+        int tile = (first_pair + j * pair_step) * 2 + crank;
+        if (tile >= num_tiles) tile = 0;  // padding tile of an odd count: stores are masked
+        const int img = tile / tiles_per_img;
+        const int h0 = (tile - img * tiles_per_img) * p.R;
+        const int buf = j % p.nbuf;
+        const uint32_t full_leader = mapa_u32(smem_u32(&slab_full[buf]), 0);
+        if (leader) mbar_arrive_expect_tx(&slab_full[buf], 2 * p.cin_chunks * p.box_bytes);
+        for (int cc = 0; cc < p.cin_chunks; ++cc)
+          tma2_load_4d(&tmX, full_leader, smem_slab + buf * slab_buf_bytes + cc * p.slab_bytes, cc * kBlockK, -1, h0 - 1, img);
+      };
+      auto run_ahead = [&](int it) {
+        while (next < n_iters && next < it + p.nbuf &&
+               mbar_try_wait(&slab_empty[next % p.nbuf], ((next / p.nbuf) & 1) ^ 1)) {
+          issue_slab(next);
+          ++next;
+        }
+      };
+      int bstage = 0;
+      uint32_t bphase = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        while (next <= it) {
+          mbar_wait(&slab_empty[next % p.nbuf], ((next / p.nbuf) & 1) ^ 1);
+          issue_slab(next);
+          ++next;
+        }
+        run_ahead(it);
+        if (!resident || it == 0) {
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&b_empty[bstage], bphase ^ 1);
+            const uint32_t bfull_leader = mapa_u32(smem_u32(&b_full[bstage]), 0);
+            if (leader) mbar_arrive_expect_tx(&b_full[bstage], 2 * kBBytes);
+            tma2_load_2d(&tmB, bfull_leader, smem_b + bstage * kBBytes, kb * kBlockK, crank * (BLOCK_N / 2));
+            if (++bstage == p.b_stages) {
+              bstage = 0;
+              bphase ^= 1;
+            }
+            run_ahead(it);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BLOCK_N);
+      int bstage = 0;
+      uint32_t bphase = 0;
+      int it = 0;
+      for (int pair = first_pair; pair < total_pairs; pair += pair_step, ++it) {
+        const int buf = it % p.nbuf;
+        const uint32_t sphase = (it / p.nbuf) & 1;
+        const int acc = it % kAcc;
+        const uint32_t acc_phase = (it / kAcc) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        mbar_wait(&slab_full[buf], sphase);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t slab_addr = smem_u32(smem_slab + buf * slab_buf_bytes);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int tap = kb / p.cin_chunks;
+          const int cc = kb - tap * p.cin_chunks;
+          const int r = tap / 3, s = tap - 3 * r;
+          if (!resident || it == 0) {
+            mbar_wait(&b_full[bstage], bphase);
+            tc_fence_after();
+          }
+          const uint32_t a_addr = slab_addr + cc * p.slab_bytes + (r * Wp + s) * 128;
+          const uint32_t b_addr = smem_u32(smem_b + bstage * kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma2_bf16_ss(tmem_d, umma_desc_sw128(a_addr + 32 * k), umma_desc_sw128(b_addr + 32 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          if (!resident) umma2_commit_pair(&b_empty[bstage]);
+          if (++bstage == p.b_stages) {
+            bstage = 0;
+            bphase ^= 1;
+          }
+        }
+        umma2_commit_pair(&slab_empty[buf]);
+        umma2_commit_pair(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..9 =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int it = 0;
+    for (int pair = first_pair; pair < total_pairs; pair += pair_step, ++it) {
+      const int tile = pair * 2 + crank;
+      const int acc = it % kAcc;
+      const uint32_t acc_phase = (it / kAcc) & 1;
+      const int i = quad * 32 + lane;           // accumulator row = padded position in the tile
+      const int ri = i / Wp, wi = i - ri * Wp;
+      const bool valid = (tile < num_tiles) && (ri < p.R) && (wi < p.W);
+      int bias_case = 0;
+      size_t m = 0;
+      if (valid) {
+        const int img = tile / tiles_per_img;
+        const int h = (tile - img * tiles_per_img) * p.R + ri;
+        m = (static_cast<size_t>(img) * p.H + h) * p.W + wi;
+        if (p.bias_cases == 9) {
+          const int rc = (h == 0) ? 0 : ((h == p.H - 1) ? 2 : 1);
+          const int cc = (wi == 0) ? 0 : ((wi == p.W - 1) ? 2 : 1);
+          bias_case = rc * 3 + cc;
+        }
+      }
+      const float* bias_row = s_bias + bias_case * BLOCK_N;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = half; c < BLOCK_N / 32; c += 2) {
+        uint32_t rr[32];
+        tmem_ld_32x32(taddr + c * 32, rr);
+        uint4 rs[4];
+        if (p.residual != nullptr && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.N + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rs[j] = __ldg(rp + j);
+        }
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+          const float4* bp = reinterpret_cast<const float4*>(bias_row + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = bp[j];
+            v[4 * j] = __uint_as_float(rr[4 * j]) + b.x;
+            v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + b.z;
+            v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + b.w;
+          }
+          if (p.prelu != nullptr) {
+            const float4* s4 = reinterpret_cast<const float4*>(s_prelu + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 sl = s4[j];
+              v[4 * j] = v[4 * j] > 0.f ? v[4 * j] : v[4 * j] * sl.x;
+              v[4 * j + 1] = v[4 * j + 1] > 0.f ? v[4 * j + 1] : v[4 * j + 1] * sl.y;
+              v[4 * j + 2] = v[4 * j + 2] > 0.f ? v[4 * j + 2] : v[4 * j + 2] * sl.z;
+              v[4 * j + 3] = v[4 * j + 3] > 0.f ? v[4 * j + 3] : v[4 * j + 3] * sl.w;
+            }
+          }
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w[4] = {rs[j].x, rs[j].y, rs[j].z, rs[j].w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                v[8 * j + 2 * t] += __uint_as_float(w[t] << 16);
+                v[8 * j + 2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
+              }
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.N + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            dst[j] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem2_dealloc(tmem_base, kAcc * BLOCK_N);
+  }
+}
+
+}  // namespace frb

@@ -104,7 +104,8 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   float* s_bias = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + 512);  // [cases][BLOCK_N]
   float* s_prelu = s_bias + 9 * BLOCK_N;                                               // [BLOCK_N]
 
-  const int warp = threadIdx.x >> 5;
+  // shuffle-broadcast makes the warp index provably warp-uniform for ptxas (uniform branches / registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int crank = static_cast<int>(cluster_ctarank());
   const bool leader = (crank == 0);
@@ -145,54 +146,73 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
+  // The producer and MMA warps run their loops CONVERGED (all 32 lanes) and only the instruction issue
+  // itself is predicated on elect.sync: inside an `if (lane == 0)` region ptxas cannot prove operands
+  // warp-uniform and wraps every TMA / UTCHMMA in an elect + R2UR.BROADCAST waterfall loop (~150 cycles of
+  // single-thread issue per MMA, which bounded every Cout <= 128 layer; see profiles/r01c).
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const int n_tile = tile % n_tiles;
-        const int m_tile = (tile / n_tiles) * 2 + crank;
-        const int m0 = (m_tile * kBlockM < p.M) ? m_tile * kBlockM : 0;  // padding tile: re-read tile 0, stores masked
-        const int pq = p.P * p.Q;
-        const int img = m0 / pq;
-        const int rem = m0 - img * pq;
-        const int pp = rem / p.Q;
-        const int qq = rem - pp * p.Q;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), 0);
+    const int pq = p.P * p.Q;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int n_tile = tile % n_tiles;
+      const int m_tile = (tile / n_tiles) * 2 + crank;
+      const int m0 = (m_tile * kBlockM < p.M) ? m_tile * kBlockM : 0;  // padding tile: re-read tile 0, stores masked
+      const int img = m0 / pq;
+      const int rem = m0 - img * pq;
+      const int pp = rem / p.Q;
+      const int qq = rem - pp * p.Q;
+      const int w_main = qq * p.stride - p.pad, h_main = pp * p.stride - p.pad;
+      const int w_sc = qq * p.sc_stride, h_sc = pp * p.sc_stride;
+      const int b_row = n_tile * BLOCK_N + crank * (BLOCK_N / 2);
+      int tap_r = 0, tap_s = 0, cc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        {
+          const uint32_t full_leader = full_leader0 + 8 * stage;
           void* sa = smem_a + stage * S::kABytes;
           void* sb = smem_b + stage * S::kBBytes;
+          if (leader && elect_one()) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
           if (kb < p.num_kb_main) {
-            const int tap = kb / p.cin_chunks;
-            const int cc = kb - tap * p.cin_chunks;
-            const int r = (p.pad ? tap / 3 : 0), s = (p.pad ? tap - 3 * (tap / 3) : 0);
-            tma2_load_im2col_4d(&tmA, full_leader, sa, cc * kBlockK, qq * p.stride - p.pad, pp * p.stride - p.pad, img,
-                                static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+            if (elect_one())
+              tma2_load_im2col_4d(&tmA, full_leader, sa, cc * kBlockK, w_main, h_main, img, static_cast<uint16_t>(tap_s),
+                                  static_cast<uint16_t>(tap_r));
           } else {
-            const int cc = kb - p.num_kb_main;
-            tma2_load_im2col_4d(&tmA2, full_leader, sa, cc * kBlockK, qq * p.sc_stride, pp * p.sc_stride, img, 0, 0);
+            if (elect_one()) tma2_load_im2col_4d(&tmA2, full_leader, sa, cc * kBlockK, w_sc, h_sc, img, 0, 0);
           }
-          tma2_load_2d(&tmB, full_leader, sb, kb * kBlockK, n_tile * BLOCK_N + crank * (BLOCK_N / 2));
-          if (++stage == S::kStages) {
-            stage = 0;
-            phase ^= 1;
+          if (elect_one()) tma2_load_2d(&tmB, full_leader, sb, kb * kBlockK, b_row);
+        }
+        __syncwarp();
+        // next K block: channel chunk fastest, then tap column, then tap row; then the shortcut chunks
+        ++cc;
+        if (kb + 1 == p.num_kb_main) {
+          cc = 0;
+        } else if (kb + 1 < p.num_kb_main && cc == p.cin_chunks) {
+          cc = 0;
+          if (++tap_s == 3) {
+            tap_s = 0;
+            ++tap_r;
           }
+        }
+        if (++stage == S::kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -200,18 +220,24 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * S::kABytes));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * S::kBBytes));
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma2_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma2_commit_pair(&empty_bar[stage]);   // frees this stage in both CTAs
+          {
+            // descriptors are computed by the converged warp (uniform datapath); each issue elects one lane
+            const uint64_t adesc = umma_desc_sw128(a_base + stage * S::kABytes);
+            const uint64_t bdesc = umma_desc_sw128(b_base + stage * S::kBBytes);
+            if (elect_one()) umma2_bf16_ss(tmem_d, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
+            if (elect_one()) umma2_bf16_ss(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+            if (elect_one()) umma2_bf16_ss(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+            if (elect_one()) umma2_bf16_ss(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+            if (elect_one()) umma2_commit_pair(&empty_bar[stage]);   // frees this stage in both CTAs
+          }
+          __syncwarp();
           if (++stage == S::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma2_commit_pair(&tmem_full_bar[acc]);   // accumulators ready in both CTAs
+        if (elect_one()) umma2_commit_pair(&tmem_full_bar[acc]);   // accumulators ready in both CTAs
+        __syncwarp();
         if (++acc == S::kAccStages) {
           acc = 0;
           acc_phase ^= 1;

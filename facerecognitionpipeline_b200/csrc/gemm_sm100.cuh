@@ -77,7 +77,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_empty_bar = tmem_full_bar + S::kAccStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + S::kAccStages);
 
-  const int warp = threadIdx.x >> 5;
+  // shuffle-broadcast makes the warp index provably warp-uniform for ptxas (uniform branches / registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   // work units ("tiles") are enumerated per cluster; CTA `crank` of a cluster takes M tile
@@ -114,7 +115,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================

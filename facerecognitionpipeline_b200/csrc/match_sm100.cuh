@@ -72,7 +72,8 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
   uint64_t* t_empty = t_full + 2;             // 2
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // shuffle-broadcast makes the warp index provably warp-uniform for ptxas (uniform branches / registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int total_items = p.p_tiles * p.slices;
 
@@ -98,7 +99,7 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
   if (warp == 0) {
     if (lane == 0) {

@@ -127,6 +127,15 @@ int frb_debug_conv(frb_ctx* ctx, const frb_layer_desc* layer, int B, const void*
 int frb_debug_im2col(frb_ctx* ctx, const void* d_in, int B, int H, int W, int C, int ksize, int stride, int pad,
                      int m0, int c0, int tap_r, int tap_s, void* d_out_16k, void* stream);
 
+/* probe: tcgen05.mma over a 128B-swizzled A operand starting j0 rows into a TMA-written slab
+ * (mode 1 sets the descriptor's base_offset field).  D[128][64] = slab[j0:j0+128] * B^T */
+int frb_debug_shift_mma(frb_ctx* ctx, const void* d_slab_256x64, const void* d_B_64x64, int j0, int mode,
+                        float* d_out_128x64, void* stream);
+
+/* probe: tcgen05.mma issue / completion cycles for `iters` back-to-back 128xNx16 MMAs (h_out2[0] = issue
+ * cycles, h_out2[1] = cycles until the commit lands); mode 0 = loop inside one lane, 1 = elect per issue */
+int frb_debug_mma_rate(frb_ctx* ctx, int N, int iters, int mode, long long* h_out2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,6 +189,14 @@ def rung_conv():
         (5, 7, 7, 512, 512, 3, 1, 9, True, 0, 0),
         (5, 14, 14, 512, 512, 3, 2, 1, False, 0, 256),
         (4, 56, 56, 64, 128, 3, 1, 9, True, 0, 0),
+        # activation-slab kernel shapes (3x3 stride 1 at W = 112 / 56 / 28), incl. odd tile counts
+        (2, 56, 56, 64, 64, 3, 1, 1, False, 1, 0),
+        (3, 56, 56, 64, 64, 3, 1, 9, True, 0, 0),
+        (3, 28, 28, 128, 128, 3, 1, 9, True, 0, 0),
+        (3, 28, 28, 128, 128, 3, 1, 1, False, 1, 0),
+        (5, 28, 28, 128, 256, 3, 1, 9, True, 0, 0),
+        (1, 112, 112, 64, 64, 3, 1, 9, True, 0, 0),
+        (37, 28, 28, 128, 128, 3, 1, 9, True, 0, 0),
     ]
     for i, c in enumerate(cases):
         r = _conv_case(ctx, *c, seed=i)

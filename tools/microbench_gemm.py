@@ -48,3 +48,7 @@ if which in ("all", "conv"):
     mode = "pair" if os.environ.get("FRB_CONV_MODE", "2") == "2" else "mcast"
     conv(256, 14, 256, 256, mode=mode); conv(290, 14, 256, 256, mode=mode); conv(97, 14, 256, 256, mode=mode); conv(1024, 14, 256, 256, mode=mode)
     conv(256, 28, 128, 128, mode=mode); conv(256, 56, 64, 64, mode=mode); conv(256, 7, 512, 512, mode=mode); conv(1024, 7, 512, 512, mode=mode)
+if which == "slab56":
+    conv(256, 56, 64, 64, mode="slab")
+if which == "slab28":
+    conv(256, 28, 128, 128, mode="slab")
