@@ -18,6 +18,7 @@
 #include "gemm2_sm100.cuh"
 #include "conv_slab_sm100.cuh"
 #include "match_sm100.cuh"
+#include "stem_sm100.cuh"
 #include "simple_kernels.cuh"
 
 using namespace frb;
@@ -277,7 +278,8 @@ bool slab_eligible(const frb_ctx* ctx, const frb_layer_desc& L, bool has_sc) {
   if (ctx->conv_mode != 2 || !ctx->use_slab) return false;
   if (L.ksize != 3 || L.stride != 1 || L.pad != 1 || has_sc) return false;
   if (L.hin != L.win || slab_rows(L.win) == 0 || L.hin % slab_rows(L.win)) return false;
-  if (L.cin % 64 || L.cin > 128 || (L.cout != 64 && L.cout != 128 && L.cout != 256)) return false;
+  // Cout = 256 (weights cannot stay resident) measured slower than the im2col pair kernel: not eligible
+  if (!((L.cin == 64 && (L.cout == 64 || L.cout == 128)) || (L.cin == 128 && L.cout == 128))) return false;
   if (L.res_buf >= 0 && (L.res_stride != 1 || L.res_h != L.hin || L.res_w != L.win)) return false;
   return true;
 }
@@ -286,52 +288,53 @@ int setup_slab(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, c
                const float* d_bias, const float* d_prelu, void* d_out, CUtensorMap* tmX, CUtensorMap* tmB,
                SlabParams* sp, int* smem_bytes, int* grid) {
   const int W = L.win, R = slab_rows(W);
+  const int chunks = L.cin / 64, num_kb = 9 * chunks;
   memset(sp, 0, sizeof(*sp));
   sp->B = B; sp->H = L.hin; sp->W = W; sp->R = R;
-  sp->cin_chunks = L.cin / 64;
   sp->N = L.cout;
-  sp->num_kb = 9 * sp->cin_chunks;
   sp->box_bytes = 128 * (W + 2) * (R + 2);
+  // the last tap's descriptor reads 128 rows starting 2 padded rows + 2 pixels into the buffer
   const int need = (128 + 2 * (W + 2) + 2) * 128;
   sp->slab_bytes = std::max((need + 1023) / 1024 * 1024, (sp->box_bytes + 1023) / 1024 * 1024);
   const int b_bytes = (L.cout / 2) * 128;
   const int misc = 1024 + 10 * L.cout * 4 + 1024;
-  const int total = 226 * 1024;
-  const int buf_bytes = sp->cin_chunks * sp->slab_bytes;
-  // Depth first: a tile is only 0.6-2.4 us of MMA work, so several slabs must be in flight to hide the
-  // ~2 us load latency.  Weights stay resident when they still fit, else they stream through a ring.
+  const int total = 227 * 1024;
+  // A unit (one 64-channel chunk of a tile's slab) is only 36 MMAs (0.6-2.4 us): several must be in flight
+  // to hide the ~2 us load latency.  Weights stay resident when three units still fit beside them.
   int nbuf, st;
-  if (sp->num_kb * b_bytes + 3 * buf_bytes + misc <= total) {
-    st = sp->num_kb;  // resident
-    nbuf = std::min(kSlabMaxBuf, (total - misc - st * b_bytes) / buf_bytes);
+  if (num_kb * b_bytes + 3 * sp->slab_bytes + misc <= total) {
+    st = num_kb;  // resident
+    nbuf = std::min(kSlabMaxBuf, (total - misc - st * b_bytes) / sp->slab_bytes);
   } else {
     nbuf = 3;
-    st = std::min(kSlabMaxBStages, (total - misc - nbuf * buf_bytes) / b_bytes);
-    if (st >= sp->num_kb) st = sp->num_kb;
+    st = std::min(kSlabMaxBStages, (total - misc - nbuf * sp->slab_bytes) / b_bytes);
+    if (st >= num_kb) st = num_kb - 1;  // == num_kb means "resident" to the kernel
   }
   if (st < 3 || nbuf < 2) return fail(ctx, "slab conv: not enough shared memory (stages %d, buffers %d)", st, nbuf);
   sp->b_stages = st;
   sp->nbuf = nbuf;
-  *smem_bytes = nbuf * buf_bytes + st * b_bytes + misc;
+  *smem_bytes = nbuf * sp->slab_bytes + st * b_bytes + misc;
   sp->bias = d_bias; sp->bias_cases = L.bias_cases;
   sp->prelu = L.has_prelu ? d_prelu : nullptr;
   sp->residual = reinterpret_cast<const __nv_bfloat16*>(d_res);
   sp->out = reinterpret_cast<__nv_bfloat16*>(d_out);
-  if (make_tmap_4d_tiled(ctx, tmX, d_in, B, L.hin, W, L.cin, W + 2, R + 2)) return 1;
-  if (make_tmap_2d(ctx, tmB, d_w, sp->num_kb * 64, L.cout, L.cout / 2)) return 1;
+  if (const char* e = getenv("FRB_SLAB_DEBUG")) sp->debug = atoi(e);
+  if (const char* e = getenv("FRB_SLAB_TRACE")) sp->trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+  if (make_tmap_4d_tiled(ctx, tmX, d_in, B, L.hin, W, L.cin, (sp->debug & 32) ? W : W + 2, (sp->debug & 16) ? 1 : R + 2)) return 1;
+  if (make_tmap_2d(ctx, tmB, d_w, num_kb * 64, (sp->debug & 64) ? 74 * L.cout : L.cout, L.cout / 2)) return 1;
   const int pairs = (B * (L.hin / R) + 1) / 2;
   *grid = std::min(pairs, ctx->num_sms / 2) * 2;
   return 0;
 }
 
-template <int BN>
+template <int BN, int CH>
 int launch_slab_t(frb_ctx* ctx, const CUtensorMap& x, const CUtensorMap& b, const SlabParams& sp, int smem_bytes, int grid,
                   cudaStream_t st) {
-  auto kern = conv_slab_sm100_kernel<BN>;
-  static int attr_bytes = 0;
-  if (attr_bytes < smem_bytes) {
+  auto kern = conv_slab_sm100_kernel<BN, CH>;
+  static bool attr_set = false;
+  if (!attr_set) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_bytes = 227 * 1024;
+    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -350,12 +353,16 @@ int launch_slab_t(frb_ctx* ctx, const CUtensorMap& x, const CUtensorMap& b, cons
   return 0;
 }
 
-int launch_slab(frb_ctx* ctx, const CUtensorMap& x, const CUtensorMap& b, const SlabParams& sp, int smem_bytes, int grid,
-                cudaStream_t st) {
-  if (sp.N == 64) return launch_slab_t<64>(ctx, x, b, sp, smem_bytes, grid, st);
-  if (sp.N == 128) return launch_slab_t<128>(ctx, x, b, sp, smem_bytes, grid, st);
-  if (sp.N == 256) return launch_slab_t<256>(ctx, x, b, sp, smem_bytes, grid, st);
-  return fail(ctx, "slab conv: unsupported Cout %d", sp.N);
+int launch_slab(frb_ctx* ctx, int chunks, const CUtensorMap& x, const CUtensorMap& b, const SlabParams& sp, int smem_bytes,
+                int grid, cudaStream_t st) {
+  if (chunks == 1) {
+    if (sp.N == 64) return launch_slab_t<64, 1>(ctx, x, b, sp, smem_bytes, grid, st);
+    if (sp.N == 128) return launch_slab_t<128, 1>(ctx, x, b, sp, smem_bytes, grid, st);
+  } else if (chunks == 2) {
+    if (sp.N == 128) return launch_slab_t<128, 2>(ctx, x, b, sp, smem_bytes, grid, st);
+    if (sp.N == 256) return launch_slab_t<256, 2>(ctx, x, b, sp, smem_bytes, grid, st);
+  }
+  return fail(ctx, "slab conv: unsupported Cin chunks %d / Cout %d", chunks, sp.N);
 }
 
 int pick_block_n(int cout) { return cout >= 256 ? 256 : (cout >= 128 ? 128 : 64); }
@@ -626,7 +633,11 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
     const frb_layer_desc& L = ctx->layers[i];
     const void* in = L.in_buf < 0 ? d_in : ctx->d_bufs[L.in_buf];
     const uint8_t* blob = ctx->d_blob;
-    if (L.op == FRB_OP_CONV) {
+    if (L.op == FRB_OP_STEM) {
+      if (L.win != 112 || L.hin % kStemRows || L.cin != 3 || L.cout != 64 || L.w_bytes != 64 * 32 * 2)
+        return fail(ctx, "stem layer must be Conv3x3(3->64) on 112-wide rows with [64][32] bf16 weights");
+      if (make_tmap_2d(ctx, &pl.tmA[i], ctx->d_bufs[L.out_buf], 64, static_cast<uint64_t>(B) * L.hin * L.win, L.win)) return 1;
+    } else if (L.op == FRB_OP_CONV) {
       const void* sc = L.sc_buf >= 0 ? ctx->d_bufs[L.sc_buf] : nullptr;
       const void* res = L.res_buf >= 0 ? ctx->d_bufs[L.res_buf] : nullptr;
       if (slab_eligible(ctx, L, sc != nullptr)) {
@@ -688,17 +699,19 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
     const uint8_t* blob = ctx->d_blob;
     if (L.op == FRB_OP_STEM) {
       const void* in = L.in_buf < 0 ? d_in : ctx->d_bufs[L.in_buf];
-      dim3 grid((L.win + 15) / 16, (L.hin + 15) / 16, Bn);
-      stem_conv_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in),
-                                             reinterpret_cast<const float*>(blob + L.w_off),
-                                             reinterpret_cast<const float*>(blob + L.bias_off),
-                                             reinterpret_cast<const float*>(blob + L.prelu_off),
-                                             ctx->d_bufs[L.out_buf], L.hin, L.win);
+      static bool attr_set = false;
+      if (!attr_set) {
+        CK(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
+        attr_set = true;
+      }
+      stem_tc_kernel<<<Bn * (L.hin / kStemRows), kStemThreads, kStemSmemBytes, st>>>(
+          pl.tmA[i], reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<const __nv_bfloat16*>(blob + L.w_off),
+          reinterpret_cast<const float*>(blob + L.bias_off), reinterpret_cast<const float*>(blob + L.prelu_off), L.hin, L.win);
       CK(cudaGetLastError());
       ctx->launches++;
     } else if (L.op == FRB_OP_CONV) {
       if (pl.use_slab[i]) {
-        if (launch_slab(ctx, pl.tmA[i], pl.tmB[i], pl.sp[i], pl.slab_smem[i], pl.grid[i], st)) return 1;
+        if (launch_slab(ctx, L.cin / 64, pl.tmA[i], pl.tmB[i], pl.sp[i], pl.slab_smem[i], pl.grid[i], st)) return 1;
       } else if (launch_conv(ctx, pl.block_n[i], pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
     } else if (L.op == FRB_OP_FC) {
       if (launch_gemm(ctx, 256, A_TILED, 1, pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
@@ -1139,7 +1152,7 @@ extern "C" int frb_debug_conv(frb_ctx* ctx, const frb_layer_desc* L, int B, cons
     SlabParams sp;
     int smem_bytes;
     if (setup_slab(ctx, LL, B, d_in, d_res, d_w, d_bias, d_prelu, d_out, &a, &b, &sp, &smem_bytes, &grid)) return 1;
-    return launch_slab(ctx, a, b, sp, smem_bytes, grid, st);
+    return launch_slab(ctx, LL.cin / 64, a, b, sp, smem_bytes, grid, st);
   }
   if (setup_conv(ctx, LL, B, d_in, d_sc, d_res, d_w, d_bias, d_prelu, d_out, &a, &a2, &b, &gp, &bn, &grid)) return 1;
   return launch_conv(ctx, bn, a, a2, b, gp, grid, st);
@@ -1297,10 +1310,11 @@ __global__ void mma_rate_kernel(int iters, int mode, long long* out) {
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tptr, 0);
   if (warp == 0) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, N);
-    const uint64_t adesc = umma_desc_sw128(smem_u32(sA));
+    // mode >= 2: A starts (mode - 2) rows (128 B each) into the buffer, i.e. not on a 1024-byte swizzle-atom boundary
+    const uint64_t adesc = umma_desc_sw128(smem_u32(sA) + (mode >= 2 ? (mode - 2) * 128 : 0));
     const uint64_t bdesc = umma_desc_sw128(smem_u32(sB));
     long long t0 = clock64();
-    if (mode == 0) {            // whole loop inside one elected lane
+    if (mode != 1) {            // whole loop inside one elected lane
       if (elect_one()) {
         for (int i = 0; i < iters; ++i) umma_bf16_ss(tmem, adesc + 2 * (i & 3), bdesc + 2 * (i & 3), idesc, i > 0 ? 1u : 0u);
         umma_commit(done);

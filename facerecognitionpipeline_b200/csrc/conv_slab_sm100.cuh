@@ -23,18 +23,18 @@ namespace frb {
 
 struct SlabParams {
   int B, H, W, R;        // images, spatial size (H == W of the layer), rows per tile
-  int cin_chunks;        // Cin / 64 (1 or 2)
   int N;                 // Cout
-  int num_kb;            // 9 * cin_chunks
-  int b_stages;          // weight ring depth; == num_kb => weights resident
-  int nbuf;              // slab buffers in flight (2..6): tiles are short, so depth hides the load latency
-  int slab_bytes;        // per (buffer, chunk), multiple of 1024
+  int b_stages;          // weight ring depth; == 9 * CHUNKS => weights resident in shared memory
+  int nbuf;              // slab-unit buffers in flight (a unit = one 64-channel chunk of one tile's slab)
+  int slab_bytes;        // per buffer, multiple of 1024
   int box_bytes;         // bytes one slab TMA box delivers
   const float* bias;     // [bias_cases][N]
   int bias_cases;
   const float* prelu;    // [N] or nullptr
   const __nv_bfloat16* residual;  // identity shortcut (same shape as out) or nullptr
   __nv_bfloat16* out;    // [B][H][W][N]
+  int debug;             // profiling experiments only (FRB_SLAB_DEBUG); 0 in production
+  long long* trace;      // [grid][16] globaltimer stamps when non-null (profiling only)
 };
 
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
@@ -47,20 +47,29 @@ __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t bar_
       : "memory");
 }
 
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SLAB_TRACE(slot) do { if (p.trace) p.trace[blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+
 constexpr int kSlabMaxBStages = 18;
 constexpr int kSlabMaxBuf = 6;
 
-template <int BLOCK_N>
+// K blocks are visited chunk-major: unit (tile, cc) runs its nine taps against weight K block tap*CHUNKS+cc,
+// so a slab buffer holds ONE 64-channel chunk and is released after 36 MMAs.
+template <int BLOCK_N, int CHUNKS>
 __global__ void __launch_bounds__(kGemm2Threads, 1)
 conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
                        const SlabParams p) {
   constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;
   constexpr int kAcc = (512 / BLOCK_N) < 4 ? (512 / BLOCK_N) : 4;  // TMEM accumulator stages
+  constexpr int kNumKb = 9 * CHUNKS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int slab_buf_bytes = p.cin_chunks * p.slab_bytes;
-  uint8_t* smem_slab = smem;                                  // [nbuf][chunks][slab_bytes]
-  uint8_t* smem_b = smem + p.nbuf * slab_buf_bytes;           // [b_stages][kBBytes]
+  uint8_t* smem_slab = smem;                                  // [nbuf][slab_bytes]
+  uint8_t* smem_b = smem + p.nbuf * p.slab_bytes;             // [b_stages][kBBytes]
   uint8_t* tail = smem_b + p.b_stages * kBBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* slab_full = bars;                             // [6]  leader only
@@ -78,13 +87,15 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   const int lane = threadIdx.x & 31;
   const int crank = static_cast<int>(cluster_ctarank());
   const bool leader = (crank == 0);
+  if (threadIdx.x == 0) SLAB_TRACE(0);
   const int Wp = p.W + 2;
   const int tiles_per_img = p.H / p.R;
   const int num_tiles = p.B * tiles_per_img;
   const int total_pairs = (num_tiles + 1) / 2;
   const int first_pair = blockIdx.x >> 1;
   const int pair_step = gridDim.x >> 1;
-  const bool resident = (p.b_stages == p.num_kb);
+  const bool resident = (p.b_stages == kNumKb);
+  const int n_iters = (total_pairs - first_pair + pair_step - 1) / pair_step;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX);
@@ -115,106 +126,170 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  if (threadIdx.x == 0) SLAB_TRACE(1);
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    // Slabs are issued as far ahead as buffers allow (up to nbuf tiles), interleaved with the weight
-    // K blocks of the current tile, so the slab depth is not throttled by the weight ring.
-    if (lane == 0) {
-      const int n_iters = (total_pairs - first_pair + pair_step - 1) / pair_step;
-      int next = 0;  // next iteration whose slab has not been issued yet
-      auto issue_slab = [&](int j) {
-        int tile = (first_pair + j * pair_step) * 2 + crank;
-        if (tile >= num_tiles) tile = 0;  // padding tile of an odd count: stores are masked
-        const int img = tile / tiles_per_img;
-        const int h0 = (tile - img * tiles_per_img) * p.R;
-        const int buf = j % p.nbuf;
-        const uint32_t full_leader = mapa_u32(smem_u32(&slab_full[buf]), 0);
-        if (leader) mbar_arrive_expect_tx(&slab_full[buf], 2 * p.cin_chunks * p.box_bytes);
-        for (int cc = 0; cc < p.cin_chunks; ++cc)
-          tma2_load_4d(&tmX, full_leader, smem_slab + buf * slab_buf_bytes + cc * p.slab_bytes, cc * kBlockK, -1, h0 - 1, img);
-      };
-      auto run_ahead = [&](int it) {
-        while (next < n_iters && next < it + p.nbuf &&
-               mbar_try_wait(&slab_empty[next % p.nbuf], ((next / p.nbuf) & 1) ^ 1)) {
-          issue_slab(next);
-          ++next;
+    // ===================== TMA producer (both CTAs; converged warp, elected issue) =====================
+    // Slab units are issued as far ahead as buffers allow, interleaved with the weight K blocks, so the
+    // slab depth is not throttled by the weight ring.
+    const int n_units = n_iters * CHUNKS;
+    const uint32_t slab_full_leader0 = mapa_u32(smem_u32(&slab_full[0]), 0);
+    const uint32_t b_full_leader0 = mapa_u32(smem_u32(&b_full[0]), 0);
+    int next = 0, nbuf_i = 0;        // next unit to issue and its buffer
+    uint32_t nphase = 0;             // parity of that buffer's use count
+    int u_it = 0, u_cc = 0;          // (iteration, chunk) of unit `next`
+    auto issue_unit = [&]() {
+      int tile = (first_pair + u_it * pair_step) * 2 + crank;
+      if (tile >= num_tiles) tile = 0;  // padding tile of an odd count: stores are masked
+      const int img = tile / tiles_per_img;
+      const int h0 = (tile - img * tiles_per_img) * p.R;
+      if (leader && elect_one()) mbar_arrive_expect_tx(&slab_full[nbuf_i], 2 * ((p.debug & 32) ? 128 * p.W * (p.R + 2) : p.box_bytes));
+      if (elect_one()) {
+        if (p.debug & 16) {  // experiment: one TMA per input row instead of one (R+2)-row box
+          for (int rr = 0; rr < p.R + 2; ++rr)
+            tma2_load_4d(&tmX, slab_full_leader0 + 8 * nbuf_i, smem_slab + nbuf_i * p.slab_bytes + rr * Wp * 128, u_cc * kBlockK,
+                         -1, h0 - 1 + rr, img);
+        } else if (p.debug & 32) {  // experiment: fully in-bounds box (wrong numerics, timing only)
+          int hh = h0 - 1;
+          hh = hh < 0 ? 0 : (hh > p.H - p.R - 2 ? p.H - p.R - 2 : hh);
+          tma2_load_4d(&tmX, slab_full_leader0 + 8 * nbuf_i, smem_slab + nbuf_i * p.slab_bytes, u_cc * kBlockK, 0, hh, img);
+        } else {
+          tma2_load_4d(&tmX, slab_full_leader0 + 8 * nbuf_i, smem_slab + nbuf_i * p.slab_bytes, u_cc * kBlockK, -1, h0 - 1, img);
         }
-      };
-      int bstage = 0;
-      uint32_t bphase = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        while (next <= it) {
-          mbar_wait(&slab_empty[next % p.nbuf], ((next / p.nbuf) & 1) ^ 1);
-          issue_slab(next);
-          ++next;
-        }
-        run_ahead(it);
-        if (!resident || it == 0) {
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+      }
+      __syncwarp();
+      ++next;
+      if (++u_cc == CHUNKS) { u_cc = 0; ++u_it; }
+      if (++nbuf_i == p.nbuf) { nbuf_i = 0; nphase ^= 1; }
+    };
+    auto run_ahead = [&]() {
+      while (next < n_units && mbar_test(&slab_empty[nbuf_i], nphase ^ 1)) issue_unit();
+    };
+    int bstage = 0;
+    uint32_t bphase = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      while (next < (it + 1) * CHUNKS) {  // this tile's units must be in flight
+        mbar_wait(&slab_empty[nbuf_i], nphase ^ 1);
+        issue_unit();
+      }
+      run_ahead();
+      if (!resident || it == 0) {
+#pragma unroll 1
+        for (int cc = 0; cc < CHUNKS; ++cc) {
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[bstage], bphase ^ 1);
-            const uint32_t bfull_leader = mapa_u32(smem_u32(&b_full[bstage]), 0);
-            if (leader) mbar_arrive_expect_tx(&b_full[bstage], 2 * kBBytes);
-            tma2_load_2d(&tmB, bfull_leader, smem_b + bstage * kBBytes, kb * kBlockK, crank * (BLOCK_N / 2));
+            if (leader && elect_one()) mbar_arrive_expect_tx(&b_full[bstage], 2 * kBBytes);
+            if (elect_one())
+              tma2_load_2d(&tmB, b_full_leader0 + 8 * bstage, smem_b + bstage * kBBytes, (tap * CHUNKS + cc) * kBlockK,
+                           crank * (BLOCK_N / 2) + ((p.debug & 64) ? (blockIdx.x >> 1) * BLOCK_N : 0));
+            __syncwarp();
             if (++bstage == p.b_stages) {
               bstage = 0;
               bphase ^= 1;
             }
-            run_ahead(it);
+            run_ahead();
           }
         }
+      } else if (next < n_units) {
+        // resident weights: nothing else to do but keep the slab ring full
+        mbar_wait(&slab_empty[nbuf_i], nphase ^ 1);
+        issue_unit();
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader only) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    // All waits run in the CONVERGED warp; the MMAs of a whole slab unit (resident weights: 36 back-to-back
+    // UTCHMMAs) or of one K block (weight ring) are issued inside ONE elect.sync region with no wait in it.
+    // ptxas only emits bare UTCHMMAs in such a branch-free single-thread region: any data-dependent branch
+    // (an mbarrier spin) inside it, an `if (lane == 0)` region, or an elect per instruction makes it wrap
+    // every UTCHMMA in an ELECT/BRA.U.ANY waterfall whose dependent predicate chain costs ~140 cycles per MMA
+    // (profiles/r01f) - 2-4x the 32-64 cycles an N <= 128 MMA takes.
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BLOCK_N);
+      const uint64_t desc0 = umma_desc_sw128(0);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t slab_lo0 = ((smem_u32(smem_slab) & 0x3FFFFu) >> 4) | static_cast<uint32_t>(desc0);
+      const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | static_cast<uint32_t>(desc0);
+      const uint32_t slab_step = static_cast<uint32_t>(p.slab_bytes) >> 4;
+      const uint32_t wp8 = static_cast<uint32_t>(Wp) * 8;  // one padded image row = Wp * 128 B
       int bstage = 0;
       uint32_t bphase = 0;
-      int it = 0;
-      for (int pair = first_pair; pair < total_pairs; pair += pair_step, ++it) {
-        const int buf = it % p.nbuf;
-        const uint32_t sphase = (it / p.nbuf) & 1;
-        const int acc = it % kAcc;
-        const uint32_t acc_phase = (it / kAcc) & 1;
+      int buf = 0;
+      uint32_t sphase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      if (resident) {
+        for (int i = 0; i < kNumKb; ++i) mbar_wait(&b_full[i], 0);  // weights land once
+      }
+      if (lane == 0) SLAB_TRACE(2);
+      for (int it = 0; it < n_iters; ++it) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-        mbar_wait(&slab_full[buf], sphase);
-        tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        const uint32_t slab_addr = smem_u32(smem_slab + buf * slab_buf_bytes);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          const int tap = kb / p.cin_chunks;
-          const int cc = kb - tap * p.cin_chunks;
-          const int r = tap / 3, s = tap - 3 * r;
-          if (!resident || it == 0) {
-            mbar_wait(&b_full[bstage], bphase);
-            tc_fence_after();
-          }
-          const uint32_t a_addr = slab_addr + cc * p.slab_bytes + (r * Wp + s) * 128;
-          const uint32_t b_addr = smem_u32(smem_b + bstage * kBBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma2_bf16_ss(tmem_d, umma_desc_sw128(a_addr + 32 * k), umma_desc_sw128(b_addr + 32 * k), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
-          if (!resident) umma2_commit_pair(&b_empty[bstage]);
-          if (++bstage == p.b_stages) {
-            bstage = 0;
-            bphase ^= 1;
+        for (int cc = 0; cc < CHUNKS; ++cc) {
+          mbar_wait(&slab_full[buf], sphase);
+          tc_fence_after();
+          if (lane == 0 && it < 4) SLAB_TRACE(3 + it);
+          const uint32_t a_lo = slab_lo0 + buf * slab_step;
+          if (resident) {
+            if (elect_one()) {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t b_lo = b_lo0 + (cc * 9 + tap) * (kBBytes >> 4);  // stages were filled in (cc, tap) order
+                const uint32_t a_tap = a_lo + (tap / 3) * wp8 + (tap % 3) * 8;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma2_bf16_ss_lo(tmem_d, a_tap + 2 * k, b_lo + 2 * k, desc_hi, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+              umma2_commit_pair(&slab_empty[buf]);
+              if (cc == CHUNKS - 1) umma2_commit_pair(&tmem_full_bar[acc]);
+            }
+            __syncwarp();
+          } else {
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_full[bstage], bphase);
+              tc_fence_after();
+              const uint32_t b_lo = b_lo0 + bstage * (kBBytes >> 4);
+              const uint32_t a_tap = a_lo + (tap / 3) * wp8 + (tap % 3) * 8;
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma2_bf16_ss_lo(tmem_d, a_tap + 2 * k, b_lo + 2 * k, desc_hi, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                umma2_commit_pair(&b_empty[bstage]);
+                if (tap == 8) {
+                  umma2_commit_pair(&slab_empty[buf]);
+                  if (cc == CHUNKS - 1) umma2_commit_pair(&tmem_full_bar[acc]);
+                }
+              }
+              __syncwarp();
+              if (++bstage == p.b_stages) {
+                bstage = 0;
+                bphase ^= 1;
+              }
+            }
+          }
+          if (++buf == p.nbuf) {
+            buf = 0;
+            sphase ^= 1;
           }
         }
-        umma2_commit_pair(&slab_empty[buf]);
-        umma2_commit_pair(&tmem_full_bar[acc]);
+        if (++acc == kAcc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
+      if (lane == 0) SLAB_TRACE(7);
     }
   } else {
     // ===================== epilogue warps 2..9 =====================
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    int it = 0;
-    for (int pair = first_pair; pair < total_pairs; pair += pair_step, ++it) {
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pair = first_pair; pair < total_pairs; pair += pair_step) {
       const int tile = pair * 2 + crank;
-      const int acc = it % kAcc;
-      const uint32_t acc_phase = (it / kAcc) & 1;
       const int i = quad * 32 + lane;           // accumulator row = padded position in the tile
       const int ri = i / Wp, wi = i - ri * Wp;
       const bool valid = (tile < num_tiles) && (ri < p.R) && (wi < p.W);
@@ -233,9 +308,11 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       const float* bias_row = s_bias + bias_case * BLOCK_N;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
+      if (threadIdx.x == 64 && pair == first_pair) SLAB_TRACE(8);
+      if (threadIdx.x == 64 && pair == first_pair + pair_step) SLAB_TRACE(9);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c = half; c < BLOCK_N / 32; c += 2) {
+      for (int c = half; c < ((p.debug & 8) ? 0 : BLOCK_N / 32); c += 2) {
         uint32_t rr[32];
         tmem_ld_32x32(taddr + c * 32, rr);
         uint4 rs[4];
@@ -245,7 +322,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           for (int j = 0; j < 4; ++j) rs[j] = __ldg(rp + j);
         }
         tmem_ld_wait();
-        if (valid) {
+        if (valid && !(p.debug & 4)) {
           float v[32];
           const float4* bp = reinterpret_cast<const float4*>(bias_row + c * 32);
 #pragma unroll
@@ -293,12 +370,18 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      if (++acc == kAcc) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
     }
   }
 
+  if (threadIdx.x == 64) SLAB_TRACE(10);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
+  if (threadIdx.x == 0) SLAB_TRACE(11);
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();

@@ -65,6 +65,53 @@ __device__ __forceinline__ void umma2_bf16_ss(uint32_t tmem_d, uint64_t adesc, u
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors given as (low word, shared high word): the low word carries the start address (>>4) and the
+// LBO bit, so stepping along K or to another filter tap is one 32-bit add on the uniform datapath
+__device__ __forceinline__ void umma2_bf16_ss_lo(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t desc_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// four K steps (one 64-wide K block) in ONE asm statement, so ptxas moves the operands to uniform registers once
+__device__ __forceinline__ void umma2_bf16_ss_lo_x4(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t desc_hi,
+                                                    uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 la, lb;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+      "add.u32 la, %1, 2;\n\t"
+      "add.u32 lb, %2, 2;\n\t"
+      "mov.b64 da, {la, %3};\n\t"
+      "mov.b64 db, {lb, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, 1;\n\t"
+      "add.u32 la, %1, 4;\n\t"
+      "add.u32 lb, %2, 4;\n\t"
+      "mov.b64 da, {la, %3};\n\t"
+      "mov.b64 db, {lb, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, 1;\n\t"
+      "add.u32 la, %1, 6;\n\t"
+      "add.u32 lb, %2, 6;\n\t"
+      "mov.b64 da, {la, %3};\n\t"
+      "mov.b64 db, {lb, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, 1;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
 __device__ __forceinline__ void umma2_commit_pair(uint64_t* bar) {  // arrive on `bar` in BOTH CTAs
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -176,15 +223,15 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t full_leader = full_leader0 + 8 * stage;
           void* sa = smem_a + stage * S::kABytes;
           void* sb = smem_b + stage * S::kBBytes;
-          if (leader && elect_one()) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-          if (kb < p.num_kb_main) {
-            if (elect_one())
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+            if (kb < p.num_kb_main)
               tma2_load_im2col_4d(&tmA, full_leader, sa, cc * kBlockK, w_main, h_main, img, static_cast<uint16_t>(tap_s),
                                   static_cast<uint16_t>(tap_r));
-          } else {
-            if (elect_one()) tma2_load_im2col_4d(&tmA2, full_leader, sa, cc * kBlockK, w_sc, h_sc, img, 0, 0);
+            else
+              tma2_load_im2col_4d(&tmA2, full_leader, sa, cc * kBlockK, w_sc, h_sc, img, 0, 0);
+            tma2_load_2d(&tmB, full_leader, sb, kb * kBlockK, b_row);
           }
-          if (elect_one()) tma2_load_2d(&tmB, full_leader, sb, kb * kBlockK, b_row);
         }
         __syncwarp();
         // next K block: channel chunk fastest, then tap column, then tap row; then the shortcut chunks
@@ -212,7 +259,10 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+      const uint64_t desc0 = umma_desc_sw128(0);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | static_cast<uint32_t>(desc0);
+      const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | static_cast<uint32_t>(desc0);
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -221,14 +271,17 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           {
-            // descriptors are computed by the converged warp (uniform datapath); each issue elects one lane
-            const uint64_t adesc = umma_desc_sw128(a_base + stage * S::kABytes);
-            const uint64_t bdesc = umma_desc_sw128(b_base + stage * S::kBBytes);
-            if (elect_one()) umma2_bf16_ss(tmem_d, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
-            if (elect_one()) umma2_bf16_ss(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
-            if (elect_one()) umma2_bf16_ss(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
-            if (elect_one()) umma2_bf16_ss(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
-            if (elect_one()) umma2_commit_pair(&empty_bar[stage]);   // frees this stage in both CTAs
+            // descriptor low words are computed by the converged warp; ONE elect region issues the K block
+            // (no branch inside it, so ptxas emits four bare UTCHMMAs + the commit; see conv_slab_sm100.cuh)
+            const uint32_t a_lo = a_lo0 + stage * (S::kABytes >> 4);
+            const uint32_t b_lo = b_lo0 + stage * (S::kBBytes >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma2_bf16_ss_lo(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma2_commit_pair(&empty_bar[stage]);   // frees this stage in both CTAs
+              if (kb == num_kb - 1) umma2_commit_pair(&tmem_full_bar[acc]);   // accumulators ready in both CTAs
+            }
           }
           __syncwarp();
           if (++stage == S::kStages) {
@@ -236,8 +289,6 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             phase ^= 1;
           }
         }
-        if (elect_one()) umma2_commit_pair(&tmem_full_bar[acc]);   // accumulators ready in both CTAs
-        __syncwarp();
         if (++acc == S::kAccStages) {
           acc = 0;
           acc_phase ^= 1;

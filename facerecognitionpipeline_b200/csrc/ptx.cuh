@@ -57,6 +57,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe.  try_wait above SUSPENDS the thread until the phase completes or a hardware time limit
+// (~4 us measured on B200) expires, so it must not be used for opportunistic polling.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a mis-programmed pipeline traps instead of hanging the GPU box
 // (a hung box is a strike). ~2^28 probes of a HW-sleeping try_wait is seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -140,73 +140,6 @@ preprocess_u8_kernel(const uint8_t* __restrict__ in, int B, int S, const unsigne
   }
 }
 
-// ------------------------------------------------------------------ stem conv 3 -> 64
-// in: [B][112][112][3] bf16, w: [27][64] fp32 (tap-major, BN folded), out: [B][112][112][64] bf16.
-// One block = 16x16 output pixels; one thread = one pixel x 64 channels.
-__global__ void __launch_bounds__(256)
-stem_conv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
-                 const float* __restrict__ bias, const float* __restrict__ prelu,
-                 __nv_bfloat16* __restrict__ out, int H, int W) {
-  __shared__ float s_in[18][18][3];
-  __shared__ __align__(16) float s_w[27][64];
-  __shared__ __align__(16) float s_bias[64];
-  __shared__ __align__(16) float s_prelu[64];
-  const int img = blockIdx.z;
-  const int ty0 = blockIdx.y * 16, tx0 = blockIdx.x * 16;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 27 * 64; i += 256) (&s_w[0][0])[i] = w[i];
-  if (tid < 64) {
-    s_bias[tid] = bias[tid];
-    s_prelu[tid] = prelu[tid];
-  }
-  const __nv_bfloat16* src = in + static_cast<size_t>(img) * H * W * 3;
-  for (int i = tid; i < 18 * 18 * 3; i += 256) {
-    const int c = i % 3, xx = (i / 3) % 18, yy = i / 54;
-    const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
-    float v = 0.f;
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-      v = __bfloat162float(src[(static_cast<size_t>(gy) * W + gx) * 3 + c]);
-    s_in[yy][xx][c] = v;
-  }
-  __syncthreads();
-  const int ly = tid >> 4, lx = tid & 15;
-  const int oy = ty0 + ly, ox = tx0 + lx;
-  float acc[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-#pragma unroll
-  for (int t = 0; t < 27; ++t) {
-    const int tap = t / 3, c = t - tap * 3;
-    const int r = tap / 3, s = tap - r * 3;
-    const float x = s_in[ly + r][lx + s][c];
-    const float4* wr = reinterpret_cast<const float4*>(&s_w[t][0]);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 ww = wr[j];
-      acc[4 * j] = fmaf(x, ww.x, acc[4 * j]);
-      acc[4 * j + 1] = fmaf(x, ww.y, acc[4 * j + 1]);
-      acc[4 * j + 2] = fmaf(x, ww.z, acc[4 * j + 2]);
-      acc[4 * j + 3] = fmaf(x, ww.w, acc[4 * j + 3]);
-    }
-  }
-  if (oy < H && ox < W) {
-    uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * H + oy) * W + ox) * 64);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        float a = acc[8 * j + t] + s_bias[8 * j + t];
-        v[t] = a > 0.f ? a : a * s_prelu[8 * j + t];
-      }
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-      dst[j] = o;
-    }
-  }
-}
-
 // ------------------------------------------------------------------ reference conv (tests only)
 // Same contract as the tcgen05 implicit-GEMM conv (GemmParams semantics), one thread per output
 // element, fp32 accumulate in K order.  Used by tests as an on-device checker for big shapes.

@@ -1,0 +1,161 @@
+// stem_sm100.cuh — input layer Conv3x3(3->64, stride 1, pad 1) + BN + PReLU on the tensor cores.
+//
+// Reference: the first module of the external AdaFace `net.Backbone.input_layer` / iresnet `conv1-bn1-prelu`
+// invoked from face_embedder.py:119,157.  K = 27 is far too thin for an im2col TMA (the
+// 3-channel pixel is 6 bytes), so the A operand is gathered by ordinary threads: one CTA owns a strip of
+// image rows; per row, thread x packs pixel x's 27 inputs (+5 zeros) into a 64-byte K-major row of a
+// 128B-swizzled shared-memory tile, one elected thread issues two 128x64x16 tcgen05.mma, and the same
+// threads run the epilogue (TMEM -> +bias -> PReLU -> bf16 -> swizzled smem tile -> one TMA store of
+// the whole 112-pixel x 64-channel row, 14 KB contiguous in NHWC).  The kernel is HBM-write bound
+// (128 B out per 6 B in); several small CTAs per SM overlap gather, MMA and store by occupancy.
+#pragma once
+#include "ptx.cuh"
+
+namespace frb {
+
+constexpr int kStemRows = 8;          // image rows per CTA
+constexpr int kStemThreads = 128;
+constexpr int kStemInStride = 352;    // bf16 elements per staged input row: 8 lead (5 unused + 1 zero pixel) + 336 + 8
+constexpr int kStemSmemBytes = 16384 /*A*/ + 8192 /*B*/ + 16384 /*out*/ + (kStemRows + 2) * kStemInStride * 2 + 512 + 64 + 1024;
+
+// w: [64][32] bf16 K-major (k = (r*3+s)*3 + c, 27..31 zero), bias/prelu: [64] fp32.
+// in: [B][H][W][3] bf16 with W == 112 (one TMEM lane per pixel of a row), out via tmOut: 2-D [B*H*W][64] bf16,
+// box 64 x W, SWIZZLE_128B.
+__global__ void __launch_bounds__(kStemThreads)
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* __restrict__ in,
+               const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+               const float* __restrict__ prelu, int H, int W) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 16384;
+  uint8_t* sOut = smem + 16384 + 8192;
+  __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(smem + 16384 + 8192 + 16384);
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sIn) + (kStemRows + 2) * kStemInStride * 2);
+  float* s_prelu = s_bias + 64;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_prelu + 64);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int strips = H / kStemRows;
+  const int img = blockIdx.x / strips;
+  const int y0 = (blockIdx.x - img * strips) * kStemRows;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmOut);
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr_smem, 64);
+    tmem_relinquish();
+  }
+  // weights -> swizzled K-major B tile (row n = output channel, four 16-byte chunks of K)
+  for (int i = tid; i < 64 * 4; i += kStemThreads) {
+    const int n = i >> 2, c = i & 3;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(w) + i);
+    *reinterpret_cast<uint4*>(sB + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+  }
+  if (tid < 64) {
+    s_bias[tid] = bias[tid];
+    s_prelu[tid] = prelu[tid];
+  }
+  // A rows 112..127 are never gathered: zero them once so the unused accumulator lanes stay finite
+  for (int i = tid; i < 16 * 8; i += kStemThreads) *reinterpret_cast<uint4*>(sA + 112 * 128 + i * 16) = make_uint4(0, 0, 0, 0);
+  // stage the strip's input rows (y0-1 .. y0+kStemRows) with zero borders
+  {
+    const int row_u4 = (W * 3 * 2) / 16;  // 42 for W = 112
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (kStemRows + 2) * (row_u4 + 2); i += kStemThreads) {
+      const int rr = i / (row_u4 + 2), j = i - rr * (row_u4 + 2);  // j = 0: lead pad, 1..row_u4: pixels, row_u4+1: tail pad
+      const int gy = y0 - 1 + rr;
+      uint4 v = z;
+      if (j >= 1 && j <= row_u4 && gy >= 0 && gy < H)
+        v = __ldg(reinterpret_cast<const uint4*>(in + (static_cast<size_t>(img) * H + gy) * W * 3) + (j - 1));
+      *reinterpret_cast<uint4*>(sIn + rr * kStemInStride + j * 8) = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+  uint32_t phase = 0;
+
+  for (int ry = 0; ry < kStemRows; ++ry) {
+    // ---- gather: pixel x = tid, K index (r*3+s)*3+c = 9 contiguous staged values per filter row r
+    if (tid < W) {
+      uint32_t pk[16];
+      unsigned short e[32];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const unsigned short* src = reinterpret_cast<const unsigned short*>(sIn + (ry + r) * kStemInStride + 5 + 3 * tid);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) e[r * 9 + q] = src[q];
+      }
+#pragma unroll
+      for (int q = 27; q < 32; ++q) e[q] = 0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) pk[q] = static_cast<uint32_t>(e[2 * q]) | (static_cast<uint32_t>(e[2 * q + 1]) << 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(sA + tid * 128 + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    }
+    if (tid == 0) tma_store_wait_read<0>();  // the previous row's store has finished reading sOut
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      umma_bf16_ss(tmem, umma_desc_sw128(a_addr), umma_desc_sw128(b_addr), idesc, 0u);
+      umma_bf16_ss(tmem, umma_desc_sw128(a_addr) + 2, umma_desc_sw128(b_addr) + 2, idesc, 1u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: thread = pixel (TMEM lane), 64 channels in two 32-column loads
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      if (tid < W) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int ch = c * 32 + j * 8 + t;
+            const float a = __uint_as_float(r[j * 8 + t]) + s_bias[ch];
+            v[t] = a > 0.f ? a : a * s_prelu[ch];
+          }
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          const int chunk = c * 4 + j;
+          *reinterpret_cast<uint4*>(sOut + tid * 128 + ((chunk ^ (tid & 7)) << 4)) = o;
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_2d(&tmOut, sOut, 0, (img * H + y0 + ry) * W);
+      tma_store_commit();
+    }
+  }
+  if (tid == 0) tma_store_wait<0>();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, 64);
+  }
+}
+
+}  // namespace frb

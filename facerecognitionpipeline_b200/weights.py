@@ -167,19 +167,21 @@ def build_program(state_dict: Dict[str, torch.Tensor], arch: str = "ir_101", lay
             setattr(L, k, v)
         return L
 
-    # ---- stem: Conv3x3(3->64) + BN + PReLU -> [27][64] fp32, t = (r*3+s)*3 + c
+    # ---- stem: Conv3x3(3->64) + BN + PReLU -> [64][32] bf16 K-major, k = (r*3+s)*3 + c, k = 27..31 zero
     a, b = _bn_affine(sd, hk["stem_bn"])
     w = sd[hk["stem_conv"]].double() * a[:, None, None, None]          # [64,3,3,3] (co,ci,r,s)
-    w_t = w.permute(2, 3, 1, 0).reshape(27, 64)                          # (r,s,ci) x co
+    w_k = torch.zeros(64, 32, dtype=torch.float64)
+    w_k[:, :27] = w.permute(0, 2, 3, 1).reshape(64, 27)                  # co x (r,s,ci)
     L = new_layer(op=FRB_OP_STEM, cin=3, cout=64, hin=112, win=112, ksize=3, stride=1, pad=1, in_buf=-1, out_buf=0,
                   has_prelu=1)
-    wb = _to_f32_bytes(w_t)
+    wb = _to_bf16_bytes(w_k)
     L.w_off, L.w_bytes = blob.add(wb), len(wb)
     L.bias_off = blob.add(_to_f32_bytes(b))
     L.prelu_off = blob.add(_to_f32_bytes(sd[hk["stem_prelu"]].double()))
     layers.append(L)
     if keep_debug:
-        debug.append(dict(kind="stem", w=w_t.float(), bias=b.float(), prelu=sd[hk["stem_prelu"]].float()))
+        w_t = w_k[:, :27].t().float().to(torch.bfloat16).float()        # [27][64], the values the device multiplies
+        debug.append(dict(kind="stem", w=w_t, bias=b.float(), prelu=sd[hk["stem_prelu"]].float()))
 
     X, Hb, Y = 0, 1, 2  # activation buffers: unit input, conv1 output, unit output
     h = 112

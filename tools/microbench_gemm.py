@@ -48,6 +48,9 @@ if which in ("all", "conv"):
     mode = "pair" if os.environ.get("FRB_CONV_MODE", "2") == "2" else "mcast"
     conv(256, 14, 256, 256, mode=mode); conv(290, 14, 256, 256, mode=mode); conv(97, 14, 256, 256, mode=mode); conv(1024, 14, 256, 256, mode=mode)
     conv(256, 28, 128, 128, mode=mode); conv(256, 56, 64, 64, mode=mode); conv(256, 7, 512, 512, mode=mode); conv(1024, 7, 512, 512, mode=mode)
+if which == "one":  # one B H Cin Cout [stride]
+    a = [int(x) for x in sys.argv[2:]]
+    conv(a[0], a[1], a[2], a[3], a[4] if len(a) > 4 else 1, mode="one")
 if which == "slab56":
     conv(256, 56, 64, 64, mode="slab")
 if which == "slab28":

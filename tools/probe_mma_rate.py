@@ -4,7 +4,7 @@ import torch
 from facerecognitionpipeline_b200 import _native
 ctx = _native.Context(0)
 out = (C.c_longlong * 2)()
-for mode in (0, 1):
+for mode in (0, 2 + 1, 2 + 2, 2 + 4, 2 + 8, 2 + 9, 2 + 58, 2 + 30):
     for N in (64, 128, 256):
         for iters in (64, 1024):
             ctx.frb_debug_mma_rate(N, iters, mode, out)
