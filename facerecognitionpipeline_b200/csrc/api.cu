@@ -51,6 +51,7 @@ struct frb_ctx {
   int driver_version = 0;
   int conv_mode = 2;  // 2 = CTA-pair kernel, 1 = 1-CTA kernel with weight multicast
   int use_slab = 1;   // activation-slab kernel for eligible 3x3 stride-1 layers (FRB_SLAB=0 disables)
+  int use_pdl = 1;    // programmatic dependent launch between backbone kernels (FRB_PDL=0 disables)
 
   // constants
   unsigned short* d_lut = nullptr;  // 256 bf16
@@ -174,6 +175,16 @@ int make_tmap_im2col(frb_ctx* ctx, CUtensorMap* m, const void* ptr, int N, int H
   return 0;
 }
 
+// cluster dimension + programmatic dependent launch (see ptx.cuh: pdl_wait)
+void fill_launch_attrs(cudaLaunchAttribute* attr, int cluster) {
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+}
+
 template <int BN, int MODE, int CL>
 int launch_gemm_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& gp,
                   int grid, cudaStream_t st) {
@@ -188,13 +199,10 @@ int launch_gemm_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, con
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = GemmSmem<BN>::kTotal;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  fill_launch_attrs(attr, CL);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ctx->use_pdl ? 2 : 1;
   CK(cudaLaunchKernelEx(&cfg, kern, a, a2, b, gp));
   ctx->launches++;
   return 0;
@@ -235,13 +243,10 @@ int launch_gemm2_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, co
   cfg.blockDim = dim3(kGemm2Threads);
   cfg.dynamicSmemBytes = Gemm2Smem<BN>::kTotal;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  fill_launch_attrs(attr, 2);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ctx->use_pdl ? 2 : 1;
   CK(cudaLaunchKernelEx(&cfg, kern, a, a2, b, gp));
   ctx->launches++;
   return 0;
@@ -341,13 +346,10 @@ int launch_slab_t(frb_ctx* ctx, const CUtensorMap& x, const CUtensorMap& b, cons
   cfg.blockDim = dim3(kGemm2Threads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  fill_launch_attrs(attr, 2);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ctx->use_pdl ? 2 : 1;
   CK(cudaLaunchKernelEx(&cfg, kern, x, b, sp));
   ctx->launches++;
   return 0;
@@ -447,6 +449,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   cudaDriverGetVersion(&ctx->driver_version);
   if (const char* e = getenv("FRB_CONV_MODE")) ctx->conv_mode = atoi(e);
   if (const char* e = getenv("FRB_SLAB")) ctx->use_slab = atoi(e);
+  if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -704,9 +707,18 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
         CK(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
         attr_set = true;
       }
-      stem_tc_kernel<<<Bn * (L.hin / kStemRows), kStemThreads, kStemSmemBytes, st>>>(
-          pl.tmA[i], reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<const __nv_bfloat16*>(blob + L.w_off),
-          reinterpret_cast<const float*>(blob + L.bias_off), reinterpret_cast<const float*>(blob + L.prelu_off), L.hin, L.win);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(Bn * (L.hin / kStemRows));
+      cfg.blockDim = dim3(kStemThreads);
+      cfg.dynamicSmemBytes = kStemSmemBytes;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[2];
+      fill_launch_attrs(attr, 1);
+      cfg.attrs = attr + 1;
+      cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+      CK(cudaLaunchKernelEx(&cfg, stem_tc_kernel, pl.tmA[i], reinterpret_cast<const __nv_bfloat16*>(in),
+                            reinterpret_cast<const __nv_bfloat16*>(blob + L.w_off), reinterpret_cast<const float*>(blob + L.bias_off),
+                            reinterpret_cast<const float*>(blob + L.prelu_off), static_cast<int>(L.hin), static_cast<int>(L.win)));
       CK(cudaGetLastError());
       ctx->launches++;
     } else if (L.op == FRB_OP_CONV) {
@@ -1344,6 +1356,87 @@ __global__ void mma_rate_kernel(int iters, int mode, long long* out) {
   }
 }
 }  // namespace
+
+// ---- same for CTA pairs (tcgen05 cta_group::2, M = 256): mode = A row offset (0 = aligned)
+namespace {
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) mma2_rate_kernel(int iters, int a_row_off, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;            // 256 x 128 B (slack for row offsets)
+  uint8_t* sB = smem + 32768;    // 128 x 128 B (half of N <= 256)
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 32768 + 16384);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const bool leader = cluster_ctarank() == 0;
+  for (int i = threadIdx.x; i < (32768 + 16384) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem2_alloc(tptr, 256);
+    tmem2_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tptr, 0);
+  if (warp == 0 && leader) {
+    constexpr uint32_t idesc = umma_idesc_bf16(256, N);
+    const uint64_t adesc = umma_desc_sw128(smem_u32(sA) + a_row_off * 128);
+    const uint64_t bdesc = umma_desc_sw128(smem_u32(sB));
+    long long t0 = clock64();
+    if (elect_one()) {
+      for (int i = 0; i < iters; ++i) umma2_bf16_ss(tmem, adesc + 2 * (i & 3), bdesc + 2 * (i & 3), idesc, i > 0 ? 1u : 0u);
+      umma2_commit_pair(done);
+    }
+    __syncwarp();
+    long long t1 = clock64();
+    mbar_wait(done, 0);
+    long long t2 = clock64();
+    if (threadIdx.x == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
+  } else if (warp == 0) {
+    mbar_wait(done, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem2_dealloc(tmem, 256);
+  }
+}
+}  // namespace
+
+extern "C" int frb_debug_mma2_rate(frb_ctx* ctx, int N, int iters, int a_row_off, long long* h_out2) {
+  if (!ctx) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  long long* d = nullptr;
+  CK(cudaMalloc(&d, 16));
+  const int smem = 32768 + 16384 + 64 + 1024;
+  if (N == 64) {
+    CK(cudaFuncSetAttribute(mma2_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma2_rate_kernel<64><<<2, 64, smem>>>(iters, a_row_off, d);
+  } else if (N == 128) {
+    CK(cudaFuncSetAttribute(mma2_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma2_rate_kernel<128><<<2, 64, smem>>>(iters, a_row_off, d);
+  } else {
+    CK(cudaFuncSetAttribute(mma2_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma2_rate_kernel<256><<<2, 64, smem>>>(iters, a_row_off, d);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(h_out2, d, 16, cudaMemcpyDeviceToHost));
+  CK(cudaFree(d));
+  return 0;
+}
 
 extern "C" int frb_debug_mma_rate(frb_ctx* ctx, int N, int iters, int mode, long long* h_out2) {
   if (!ctx) return 1;

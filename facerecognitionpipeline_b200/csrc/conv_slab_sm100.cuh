@@ -34,7 +34,7 @@ struct SlabParams {
   const __nv_bfloat16* residual;  // identity shortcut (same shape as out) or nullptr
   __nv_bfloat16* out;    // [B][H][W][N]
   int debug;             // profiling experiments only (FRB_SLAB_DEBUG); 0 in production
-  long long* trace;      // [grid][16] globaltimer stamps when non-null (profiling only)
+  long long* trace;      // [grid][128] globaltimer stamps when non-null (profiling only)
 };
 
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
@@ -52,7 +52,7 @@ __device__ __forceinline__ long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define SLAB_TRACE(slot) do { if (p.trace) p.trace[blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+#define SLAB_TRACE(slot) do { if (p.trace) p.trace[blockIdx.x * 128 + (slot)] = gtimer(); } while (0)
 
 constexpr int kSlabMaxBStages = 18;
 constexpr int kSlabMaxBuf = 6;
@@ -127,6 +127,10 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
   if (threadIdx.x == 0) SLAB_TRACE(1);
+  pdl_launch_dependents();
+  // Everything above (and the resident weight loads below) is independent of the previous layer; the producer
+  // waits for it just before its first activation load, the epilogue warps before their first residual read / store.
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; converged warp, elected issue) =====================
@@ -167,22 +171,37 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     };
     int bstage = 0;
     uint32_t bphase = 0;
+    if (resident) {
+      // weights do not depend on the previous layer: fetch them before waiting for it
+      for (int cc = 0; cc < CHUNKS; ++cc)
+        for (int tap = 0; tap < 9; ++tap) {
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&b_full[bstage], 2 * kBBytes);
+            tma2_load_2d(&tmB, b_full_leader0 + 8 * bstage, smem_b + bstage * kBBytes, (tap * CHUNKS + cc) * kBlockK,
+                         crank * (BLOCK_N / 2) + ((p.debug & 64) ? (blockIdx.x >> 1) * BLOCK_N : 0));
+          }
+          __syncwarp();
+          ++bstage;
+        }
+    }
+    pdl_wait();
     for (int it = 0; it < n_iters; ++it) {
       while (next < (it + 1) * CHUNKS) {  // this tile's units must be in flight
         mbar_wait(&slab_empty[nbuf_i], nphase ^ 1);
         issue_unit();
       }
       run_ahead();
-      if (!resident || it == 0) {
+      if (!resident) {
 #pragma unroll 1
         for (int cc = 0; cc < CHUNKS; ++cc) {
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[bstage], bphase ^ 1);
-            if (leader && elect_one()) mbar_arrive_expect_tx(&b_full[bstage], 2 * kBBytes);
-            if (elect_one())
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(&b_full[bstage], 2 * kBBytes);
               tma2_load_2d(&tmB, b_full_leader0 + 8 * bstage, smem_b + bstage * kBBytes, (tap * CHUNKS + cc) * kBlockK,
-                           crank * (BLOCK_N / 2) + ((p.debug & 64) ? (blockIdx.x >> 1) * BLOCK_N : 0));
+                           crank * (BLOCK_N / 2));
+            }
             __syncwarp();
             if (++bstage == p.b_stages) {
               bstage = 0;
@@ -225,12 +244,14 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       if (lane == 0) SLAB_TRACE(2);
       for (int it = 0; it < n_iters; ++it) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        if (lane == 0 && it < 28) SLAB_TRACE(16 + it * 4);
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
 #pragma unroll
         for (int cc = 0; cc < CHUNKS; ++cc) {
           mbar_wait(&slab_full[buf], sphase);
           tc_fence_after();
           if (lane == 0 && it < 4) SLAB_TRACE(3 + it);
+          if (lane == 0 && it < 28) SLAB_TRACE(16 + it * 4 + 1 + cc);
           const uint32_t a_lo = slab_lo0 + buf * slab_step;
           if (resident) {
             if (elect_one()) {

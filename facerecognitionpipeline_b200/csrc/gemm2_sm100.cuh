@@ -194,6 +194,8 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // the prologue above overlapped the previous layer's tail; its output is needed from here on
 
   // The producer and MMA warps run their loops CONVERGED (all 32 lanes) and only the instruction issue
   // itself is predicated on elect.sync: inside an `if (lane == 0)` region ptxas cannot prove operands

@@ -116,6 +116,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (CLUSTER > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================

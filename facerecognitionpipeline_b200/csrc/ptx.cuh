@@ -26,6 +26,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels of the backbone are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's CTAs may
+// become resident (as SMs drain) while the previous layer is still finishing its tail, run their prologue (barrier
+// init, TMEM allocation, bias / resident-weight loads: nothing that depends on the previous layer) and then block
+// in pdl_wait() until the previous grid has fully completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

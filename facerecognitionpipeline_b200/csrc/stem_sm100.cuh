@@ -63,6 +63,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
   }
   // A rows 112..127 are never gathered: zero them once so the unused accumulator lanes stay finite
   for (int i = tid; i < 16 * 8; i += kStemThreads) *reinterpret_cast<uint4*>(sA + 112 * 128 + i * 16) = make_uint4(0, 0, 0, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // the input tensor is written by the preprocessing / warp kernel launched just before
   // stage the strip's input rows (y0-1 .. y0+kStemRows) with zero borders
   {
     const int row_u4 = (W * 3 * 2) / 16;  // 42 for W = 112

@@ -135,6 +135,8 @@ int frb_debug_shift_mma(frb_ctx* ctx, const void* d_slab_256x64, const void* d_B
 /* probe: tcgen05.mma issue / completion cycles for `iters` back-to-back 128xNx16 MMAs (h_out2[0] = issue
  * cycles, h_out2[1] = cycles until the commit lands); mode 0 = loop inside one lane, 1 = elect per issue */
 int frb_debug_mma_rate(frb_ctx* ctx, int N, int iters, int mode, long long* h_out2);
+/* same for CTA pairs (cta_group::2, 256 x N x 16); a_row_off = A start offset in 128-byte rows */
+int frb_debug_mma2_rate(frb_ctx* ctx, int N, int iters, int a_row_off, long long* h_out2);
 
 #ifdef __cplusplus
 }
