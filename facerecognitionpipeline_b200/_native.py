@@ -70,6 +70,7 @@ SIGNATURES = {
     "frb_embed_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "frb_match_host": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     "frb_embed_match_host": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "frb_embed_profile": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "frb_debug_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "frb_debug_conv": (_i, [_vp, C.POINTER(LayerDesc), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "frb_debug_shift_mma": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),

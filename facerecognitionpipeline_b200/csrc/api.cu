@@ -71,6 +71,8 @@ struct frb_ctx {
   size_t emb2_elems = 0;
   Plan plan;
   double flops_per_face = 0.0;
+  bool profiling = false;               // frb_embed_profile: CUDA events around every layer launch
+  std::vector<cudaEvent_t> prof_events;
 
   // gallery
   float* d_gal = nullptr;
@@ -697,9 +699,18 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
     ctx->plan.d_in = d_in;
   }
   Plan& pl = ctx->plan;
+  if (ctx->profiling) {
+    while (ctx->prof_events.size() < ctx->layers.size() + 1) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      ctx->prof_events.push_back(e);
+    }
+    CK(cudaEventRecord(ctx->prof_events[0], st));
+  }
   for (size_t i = 0; i < ctx->layers.size(); ++i) {
     const frb_layer_desc& L = ctx->layers[i];
     const uint8_t* blob = ctx->d_blob;
+    if (ctx->profiling && i > 0) CK(cudaEventRecord(ctx->prof_events[i], st));
     if (L.op == FRB_OP_STEM) {
       const void* in = L.in_buf < 0 ? d_in : ctx->d_bufs[L.in_buf];
       static bool attr_set = false;
@@ -756,10 +767,50 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
       }
     }
   }
+  if (ctx->profiling) CK(cudaEventRecord(ctx->prof_events[ctx->layers.size()], st));
   return 0;
 }
 
 }  // namespace
+
+// Profiling variant of frb_embed: the same launches with a CUDA event between consecutive layers (which also
+// serialises them: no programmatic overlap), so per-layer durations can be read back.  kernel_id: 0 stem,
+// 1/2/3 = CTA-pair im2col conv with Cout tile 64/128/256, 4/5/6 = slab conv <64,1>/<128,1>/<128,2>, 7 = FC + finalize.
+extern "C" int frb_embed_profile(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, void* stream,
+                                 float* h_layer_ms, int* h_kernel_id, double* h_layer_flops, int max_layers,
+                                 int* n_layers) {
+  if (!ctx) return 1;
+  if (B <= 0) return 0;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ctx->profiling = true;
+  const int rc = embed_locked(ctx, d_in, B, flags, d_emb, nullptr, nullptr, st);
+  ctx->profiling = false;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(st));
+  const int nl = static_cast<int>(ctx->layers.size());
+  const int Bn = (flags & FRB_EMBED_FLIP) ? 2 * B : B;
+  if (n_layers) *n_layers = nl;
+  for (int i = 0; i < nl && i < max_layers; ++i) {
+    const frb_layer_desc& L = ctx->layers[i];
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+    if (h_layer_ms) h_layer_ms[i] = ms;
+    int id = 7;
+    if (L.op == FRB_OP_STEM) id = 0;
+    else if (L.op == FRB_OP_CONV) {
+      if (ctx->plan.use_slab[i]) id = L.cout == 64 ? 4 : (L.cin == 64 ? 5 : 6);
+      else id = ctx->plan.block_n[i] == 64 ? 1 : (ctx->plan.block_n[i] == 128 ? 2 : 3);
+    }
+    if (h_kernel_id) h_kernel_id[i] = id;
+    const int P = out_dim(L.hin, L.ksize, L.stride, L.pad), Q = out_dim(L.win, L.ksize, L.stride, L.pad);
+    double fl = L.op == FRB_OP_FC ? 2.0 * L.cin * L.cout
+                                  : 2.0 * P * Q * L.cout * (static_cast<double>(L.ksize) * L.ksize * L.cin + (L.sc_buf >= 0 ? L.sc_cin : 0));
+    if (h_layer_flops) h_layer_flops[i] = fl * Bn;
+  }
+  return 0;
+}
 
 extern "C" int frb_embed(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, float* d_norm,
                          void* d_emb_bf16, void* stream) {

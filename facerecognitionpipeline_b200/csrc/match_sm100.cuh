@@ -101,71 +101,85 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
+  // Producer and MMA warps run CONVERGED; every wait is outside the elect.sync regions that issue TMA / UTCHMMA, so
+  // ptxas emits bare back-to-back instructions (see conv_slab_sm100.cuh for the measurement behind this).
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, a_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int pt = item % p.p_tiles;
-        const int gs = item / p.p_tiles;
-        const int t_begin = gs * p.tiles_per_slice;
-        const int t_end = min(p.g_tiles, t_begin + p.tiles_per_slice);
-        // probe tile: wait until the previous item's MMAs no longer read it
-        mbar_wait(a_empty, a_phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0, a_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int pt = item % p.p_tiles;
+      const int gs = item / p.p_tiles;
+      const int t_begin = gs * p.tiles_per_slice;
+      const int t_end = min(p.g_tiles, t_begin + p.tiles_per_slice);
+      // probe tile: wait until the previous item's MMAs no longer read it
+      mbar_wait(a_empty, a_phase ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(a_full, kMatchKB * S::kABytes);
+#pragma unroll
         for (int kb = 0; kb < kMatchKB; ++kb)
           tma_load_2d(&tmP, a_full, smem_a + kb * S::kABytes, kb * 64, pt * 128);
-        a_phase ^= 1;
-        for (int t = t_begin; t < t_end; ++t) {
-          for (int kb = 0; kb < kMatchKB; ++kb) {
-            mbar_wait(&b_empty[stage], phase ^ 1);
+      }
+      __syncwarp();
+      a_phase ^= 1;
+      for (int t = t_begin; t < t_end; ++t) {
+#pragma unroll 1
+        for (int kb = 0; kb < kMatchKB; ++kb) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&b_full[stage], S::kBBytes);
             tma_load_2d(&tmG, &b_full[stage], smem_b + stage * S::kBBytes, kb * 64, t * kMatchBN);
-            if (++stage == kMatchBStages) {
-              stage = 0;
-              phase ^= 1;
-            }
+          }
+          __syncwarp();
+          if (++stage == kMatchBStages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, kMatchBN);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0, a_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int gs = item / p.p_tiles;
-        const int t_begin = gs * p.tiles_per_slice;
-        const int t_end = min(p.g_tiles, t_begin + p.tiles_per_slice);
-        mbar_wait(a_full, a_phase);
-        a_phase ^= 1;
-        tc_fence_after();
-        for (int t = t_begin; t < t_end; ++t) {
-          mbar_wait(&t_empty[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, kMatchBN);
+    const uint64_t desc0 = umma_desc_sw128(0);
+    const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+    const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | static_cast<uint32_t>(desc0);
+    const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | static_cast<uint32_t>(desc0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int gs = item / p.p_tiles;
+      const int t_begin = gs * p.tiles_per_slice;
+      const int t_end = min(p.g_tiles, t_begin + p.tiles_per_slice);
+      mbar_wait(a_full, a_phase);
+      a_phase ^= 1;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&t_empty[acc], acc_phase ^ 1);
+        const uint32_t tmem_d = tmem_base + acc * kMatchBN;
+#pragma unroll 1
+        for (int kb = 0; kb < kMatchKB; ++kb) {
+          mbar_wait(&b_full[stage], phase);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + acc * kMatchBN;
-          for (int kb = 0; kb < kMatchKB; ++kb) {
-            mbar_wait(&b_full[stage], phase);
-            tc_fence_after();
-            const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + kb * S::kABytes));
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * S::kBBytes));
+          const uint32_t a_lo = a_lo0 + kb * (S::kABytes >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (S::kBBytes >> 4);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_ss_lo(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             umma_commit(&b_empty[stage]);
-            if (++stage == kMatchBStages) {
-              stage = 0;
-              phase ^= 1;
+            if (kb == kMatchKB - 1) {
+              umma_commit(&t_full[acc]);
+              if (t == t_end - 1) umma_commit(a_empty);  // all MMAs reading this probe tile have retired
             }
           }
-          umma_commit(&t_full[acc]);
-          if (++acc == 2) {
-            acc = 0;
-            acc_phase ^= 1;
+          __syncwarp();
+          if (++stage == kMatchBStages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
-        umma_commit(a_empty);  // all MMAs reading this probe tile have retired
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
     }
   } else {

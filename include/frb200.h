@@ -87,6 +87,11 @@ int frb_backbone_load(frb_ctx* ctx, const frb_layer_desc* layers, int n_layers, 
 int frb_embed(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, float* d_norm,
               void* d_emb_bf16, void* stream);
 double frb_backbone_flops_per_face(frb_ctx* ctx);
+/* measurement aid (bench.py roofline): frb_embed with a CUDA event between consecutive layers; per layer the
+ * duration (ms), the kernel that ran it (0 stem, 1/2/3 CTA-pair im2col conv with Cout tile 64/128/256,
+ * 4/5/6 slab conv <64,1>/<128,1>/<128,2>, 7 FC + finalize) and its FLOPs for this batch. */
+int frb_embed_profile(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, void* stream,
+                      float* h_layer_ms, int* h_kernel_id, double* h_layer_flops, int max_layers, int* n_layers);
 
 /* ---- gallery ---- */
 /* g: [N][512] f32 rows (NOT re-normalised, as in search()); is_device selects the pointer kind.
