@@ -29,6 +29,7 @@ namespace {
 
 struct Plan {  // per-batch-size launch plan of the backbone
   int B = 0;
+  bool dataflow = false;
   const void* d_in = nullptr;  // the descriptors bake in the batch size and the input pointer
   std::vector<CUtensorMap> tmA, tmA2, tmB;
   std::vector<GemmParams> gp;
@@ -36,6 +37,7 @@ struct Plan {  // per-batch-size launch plan of the backbone
   std::vector<int> use_slab;       // 1 = conv_slab_sm100_kernel (3x3 stride-1, W in {28,56,112})
   std::vector<SlabParams> sp;
   std::vector<int> slab_smem;
+  std::vector<int> wait_target;    // dataflow: progress units every image must have before this layer may read it
 };
 
 }  // namespace
@@ -52,6 +54,9 @@ struct frb_ctx {
   int conv_mode = 2;  // 2 = CTA-pair kernel, 1 = 1-CTA kernel with weight multicast
   int use_slab = 1;   // activation-slab kernel for eligible 3x3 stride-1 layers (FRB_SLAB=0 disables)
   int use_pdl = 1;    // programmatic dependent launch between backbone kernels (FRB_PDL=0 disables)
+  int use_dataflow = 0;  // per-image progress counters instead of whole-grid dependencies (FRB_DATAFLOW=0 disables; needs PDL)
+  int* d_progress = nullptr;
+  int progress_cap = 0;
 
   // constants
   unsigned short* d_lut = nullptr;  // 256 bf16
@@ -286,7 +291,7 @@ bool slab_eligible(const frb_ctx* ctx, const frb_layer_desc& L, bool has_sc) {
   if (L.ksize != 3 || L.stride != 1 || L.pad != 1 || has_sc) return false;
   if (L.hin != L.win || slab_rows(L.win) == 0 || L.hin % slab_rows(L.win)) return false;
   // Cout = 256 (weights cannot stay resident) measured slower than the im2col pair kernel: not eligible
-  if (!((L.cin == 64 && (L.cout == 64 || L.cout == 128)) || (L.cin == 128 && L.cout == 128))) return false;
+  if (!((L.cin == 64 && (L.cout == 64 || L.cout == 128)) || (L.cin == 128 && (L.cout == 128 || (L.cout == 256 && getenv("FRB_SLAB_N256")))))) return false;
   if (L.res_buf >= 0 && (L.res_stride != 1 || L.res_h != L.hin || L.res_w != L.win)) return false;
   return true;
 }
@@ -452,6 +457,8 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_CONV_MODE")) ctx->conv_mode = atoi(e);
   if (const char* e = getenv("FRB_SLAB")) ctx->use_slab = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
+  if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
+  if (!ctx->use_pdl) ctx->use_dataflow = 0;
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -516,7 +523,7 @@ extern "C" void frb_ctx_destroy(frb_ctx* ctx) {
                   ctx->d_gal_maxnorm, ctx->d_probe_f32, ctx->d_probe_bf16, ctx->d_cand_score, ctx->d_cand_idx,
                   ctx->d_flagged, ctx->d_flag_rows, ctx->d_exact, ctx->d_scores64_tmp, ctx->d_stage_u8,
                   ctx->d_stage_in, ctx->d_stage_emb, ctx->d_stage_norm, ctx->d_stage_sc, ctx->d_stage_idx,
-                  ctx->d_stage_acc, ctx->d_jobs};
+                  ctx->d_stage_acc, ctx->d_jobs, ctx->d_progress};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto* b : ctx->d_bufs)
@@ -631,6 +638,23 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
   }
   const size_t nl = ctx->layers.size();
   Plan& pl = ctx->plan;
+  if (ctx->progress_cap < B) {
+    if (ctx->d_progress) CK(cudaFree(ctx->d_progress));
+    ctx->d_progress = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_progress), sizeof(int) * B));
+    ctx->progress_cap = B;
+  }
+  pl.wait_target.assign(nl, 0);
+  {
+    long long units = 0;  // (output row x 32-channel chunk) units per image written by the layers so far
+    for (size_t i = 0; i < nl; ++i) {
+      const frb_layer_desc& L = ctx->layers[i];
+      pl.wait_target[i] = static_cast<int>(units);
+      if (L.op != FRB_OP_FC)
+        units += static_cast<long long>(out_dim(L.hin, L.ksize, L.stride, L.pad)) * out_dim(L.win, L.ksize, L.stride, L.pad) * (L.cout / 32);
+    }
+    if (units > 0x7fffffffLL) return fail(ctx, "dataflow progress counter would overflow");
+  }
   pl.B = B;
   pl.tmA.resize(nl); pl.tmA2.resize(nl); pl.tmB.resize(nl); pl.gp.resize(nl); pl.block_n.assign(nl, 0); pl.grid.assign(nl, 0);
   pl.use_slab.assign(nl, 0); pl.sp.resize(nl); pl.slab_smem.assign(nl, 0);
@@ -653,12 +677,22 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
           return 1;
         memset(&pl.gp[i], 0, sizeof(GemmParams));
         pl.gp[i].M = 1;  // plan marker: non-empty
+        if (ctx->use_dataflow && !ctx->profiling) {
+          pl.sp[i].progress = ctx->d_progress;
+          pl.sp[i].wait_target = ctx->use_dataflow == 2 ? -1 : pl.wait_target[i];
+          pl.sp[i].sig_fence = getenv("FRB_DF_NOFENCE") ? 0 : 1;
+        }
         continue;
       }
       if (setup_conv(ctx, L, B, in, sc, res, blob + L.w_off, reinterpret_cast<const float*>(blob + L.bias_off),
                      reinterpret_cast<const float*>(blob + L.prelu_off), ctx->d_bufs[L.out_buf], &pl.tmA[i],
                      &pl.tmA2[i], &pl.tmB[i], &pl.gp[i], &pl.block_n[i], &pl.grid[i]))
         return 1;
+      if (ctx->use_dataflow && !ctx->profiling && ctx->conv_mode == 2) {
+        pl.gp[i].progress = ctx->d_progress;
+        pl.gp[i].wait_target = ctx->use_dataflow == 2 ? -1 : pl.wait_target[i];
+        pl.gp[i].sig_fence = getenv("FRB_DF_NOFENCE") ? 0 : 1;
+      }
     } else if (L.op == FRB_OP_FC) {
       if (L.cin % 64 || L.cout % 256) return fail(ctx, "FC dims unsupported (%d -> %d)", L.cin, L.cout);
       GemmParams& gp = pl.gp[i];
@@ -693,12 +727,16 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
                  cudaStream_t st) {
   if (ctx->layers.empty()) return fail(ctx, "frb_embed: no backbone loaded");
   const int Bn = (flags & FRB_EMBED_FLIP) ? 2 * B : B;  // faces through the network
-  if (ctx->plan.B != Bn || ctx->plan.d_in != d_in || ctx->plan.gp.empty()) {
+  const bool want_df = ctx->use_dataflow && !ctx->profiling;
+  if (ctx->plan.B != Bn || ctx->plan.d_in != d_in || ctx->plan.gp.empty() || ctx->plan.dataflow != want_df) {
     ctx->plan.gp.clear();
     if (build_plan(ctx, Bn, d_in)) return 1;
     ctx->plan.d_in = d_in;
+    ctx->plan.dataflow = want_df;
   }
   Plan& pl = ctx->plan;
+  const bool dataflow = pl.dataflow && ctx->conv_mode == 2;
+  if (dataflow) CK(cudaMemsetAsync(ctx->d_progress, 0, sizeof(int) * Bn, st));
   if (ctx->profiling) {
     while (ctx->prof_events.size() < ctx->layers.size() + 1) {
       cudaEvent_t e;
@@ -729,7 +767,8 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
       cfg.numAttrs = ctx->use_pdl ? 1 : 0;
       CK(cudaLaunchKernelEx(&cfg, stem_tc_kernel, pl.tmA[i], reinterpret_cast<const __nv_bfloat16*>(in),
                             reinterpret_cast<const __nv_bfloat16*>(blob + L.w_off), reinterpret_cast<const float*>(blob + L.bias_off),
-                            reinterpret_cast<const float*>(blob + L.prelu_off), static_cast<int>(L.hin), static_cast<int>(L.win)));
+                            reinterpret_cast<const float*>(blob + L.prelu_off), static_cast<int>(L.hin), static_cast<int>(L.win),
+                            dataflow ? ctx->d_progress : static_cast<int*>(nullptr)));
       CK(cudaGetLastError());
       ctx->launches++;
     } else if (L.op == FRB_OP_CONV) {

@@ -35,6 +35,9 @@ struct SlabParams {
   __nv_bfloat16* out;    // [B][H][W][N]
   int debug;             // profiling experiments only (FRB_SLAB_DEBUG); 0 in production
   long long* trace;      // [grid][128] globaltimer stamps when non-null (profiling only)
+  int* progress;         // inter-layer dataflow counters (ptx.cuh); nullptr = whole-grid dependency
+  int wait_target;
+  int sig_fence;         // experiments only: 0 drops the release fence (UNSAFE)
 };
 
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
@@ -53,6 +56,13 @@ __device__ __forceinline__ long long gtimer() {
   return t;
 }
 #define SLAB_TRACE(slot) do { if (p.trace) p.trace[blockIdx.x * 128 + (slot)] = gtimer(); } while (0)
+
+// L2 prefetch of a tiled box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 
 constexpr int kSlabMaxBStages = 18;
 constexpr int kSlabMaxBuf = 6;
@@ -130,7 +140,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   pdl_launch_dependents();
   // Everything above (and the resident weight loads below) is independent of the previous layer; the producer
   // waits for it just before its first activation load, the epilogue warps before their first residual read / store.
-  if (warp != 0) pdl_wait();
+  if (warp != 0 && (p.progress == nullptr || p.wait_target < 0)) pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; converged warp, elected issue) =====================
@@ -147,6 +157,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       if (tile >= num_tiles) tile = 0;  // padding tile of an odd count: stores are masked
       const int img = tile / tiles_per_img;
       const int h0 = (tile - img * tiles_per_img) * p.R;
+      if (p.progress != nullptr && p.wait_target >= 0 && u_cc == 0) wait_images(p.progress, img, img, p.wait_target);
       if (leader && elect_one()) mbar_arrive_expect_tx(&slab_full[nbuf_i], 2 * ((p.debug & 32) ? 128 * p.W * (p.R + 2) : p.box_bytes));
       if (elect_one()) {
         if (p.debug & 16) {  // experiment: one TMA per input row instead of one (R+2)-row box
@@ -159,6 +170,17 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           tma2_load_4d(&tmX, slab_full_leader0 + 8 * nbuf_i, smem_slab + nbuf_i * p.slab_bytes, u_cc * kBlockK, 0, hh, img);
         } else {
           tma2_load_4d(&tmX, slab_full_leader0 + 8 * nbuf_i, smem_slab + nbuf_i * p.slab_bytes, u_cc * kBlockK, -1, h0 - 1, img);
+        }
+      }
+      if ((p.debug & 128) && elect_one()) {
+        // pull the unit that will reuse this buffer (nbuf units ahead) into L2 now: its real load then hits L2
+        const int f_unit = next + p.nbuf;
+        const int f_it = f_unit / CHUNKS, f_cc = f_unit - f_it * CHUNKS;
+        int f_tile = (first_pair + f_it * pair_step) * 2 + crank;
+        if (f_it < n_iters && f_tile < num_tiles) {
+          const int f_img = f_tile / tiles_per_img;
+          const int f_h0 = (f_tile - f_img * tiles_per_img) * p.R;
+          tma_prefetch_4d(&tmX, f_cc * kBlockK, -1, f_h0 - 1, f_img);
         }
       }
       __syncwarp();
@@ -184,10 +206,10 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           ++bstage;
         }
     }
-    pdl_wait();
+    if (p.progress == nullptr || p.wait_target < 0) pdl_wait();
     for (int it = 0; it < n_iters; ++it) {
       while (next < (it + 1) * CHUNKS) {  // this tile's units must be in flight
-        mbar_wait(&slab_empty[nbuf_i], nphase ^ 1);
+        if (p.debug & 256) { while (!mbar_test(&slab_empty[nbuf_i], nphase ^ 1)) {} } else mbar_wait(&slab_empty[nbuf_i], nphase ^ 1);
         issue_unit();
       }
       run_ahead();
@@ -212,7 +234,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
       } else if (next < n_units) {
         // resident weights: nothing else to do but keep the slab ring full
-        mbar_wait(&slab_empty[nbuf_i], nphase ^ 1);
+        if (p.debug & 256) { while (!mbar_test(&slab_empty[nbuf_i], nphase ^ 1)) {} } else mbar_wait(&slab_empty[nbuf_i], nphase ^ 1);
         issue_unit();
       }
     }
@@ -314,10 +336,10 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       const int i = quad * 32 + lane;           // accumulator row = padded position in the tile
       const int ri = i / Wp, wi = i - ri * Wp;
       const bool valid = (tile < num_tiles) && (ri < p.R) && (wi < p.W);
-      int bias_case = 0;
+      int bias_case = 0, img = 0;
       size_t m = 0;
       if (valid) {
-        const int img = tile / tiles_per_img;
+        img = tile / tiles_per_img;
         const int h = (tile - img * tiles_per_img) * p.R + ri;
         m = (static_cast<size_t>(img) * p.H + h) * p.W + wi;
         if (p.bias_cases == 9) {
@@ -391,6 +413,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      if (p.progress != nullptr) signal_rows(p.progress, valid, img, BLOCK_N / 64, p.sig_fence != 0);
       if (++acc == kAcc) {
         acc = 0;
         acc_phase ^= 1;

@@ -195,7 +195,9 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
   pdl_launch_dependents();
-  pdl_wait();  // the prologue above overlapped the previous layer's tail; its output is needed from here on
+  // the prologue above overlapped the previous layer's tail.  Without progress counters the whole previous grid
+  // must have finished; with them each tile waits only for the images it reads (producer warp, below).
+  if (p.progress == nullptr || p.wait_target < 0) pdl_wait();
 
   // The producer and MMA warps run their loops CONVERGED (all 32 lanes) and only the instruction issue
   // itself is predicated on elect.sync: inside an `if (lane == 0)` region ptxas cannot prove operands
@@ -218,6 +220,10 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int w_main = qq * p.stride - p.pad, h_main = pp * p.stride - p.pad;
       const int w_sc = qq * p.sc_stride, h_sc = pp * p.sc_stride;
       const int b_row = n_tile * BLOCK_N + crank * (BLOCK_N / 2);
+      if (p.progress != nullptr && p.wait_target >= 0) {
+        const int m_last = min(m0 + kBlockM, p.M) - 1;
+        wait_images(p.progress, img, m_last / pq, p.wait_target);
+      }
       int tap_r = 0, tap_s = 0, cc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -312,11 +318,11 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int m = m_tile * kBlockM + row;
       const bool valid = m < p.M;
       const int n0 = n_tile * BLOCK_N;
-      int bias_case = 0;
+      int bias_case = 0, img = 0;
       size_t res_off = 0;
       if (valid) {
         const int pq = p.P * p.Q;
-        const int img = m / pq;
+        img = m / pq;
         const int rem = m - img * pq;
         const int pp = rem / p.Q;
         const int qq = rem - pp * p.Q;
@@ -401,6 +407,7 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      if (p.progress != nullptr) signal_rows(p.progress, valid, img, BLOCK_N / 64, p.sig_fence != 0);  // this warp stored BLOCK_N/64 chunks per row
       if (++acc == S::kAccStages) {
         acc = 0;
         acc_phase ^= 1;

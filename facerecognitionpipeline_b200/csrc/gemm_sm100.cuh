@@ -42,6 +42,10 @@ struct GemmParams {
   int res_stride, RH, RW;
   __nv_bfloat16* out;             // [M, N] bf16 (nullptr when out_f32 is used)
   float* out_f32;                 // [num_splits][M][N] fp32 raw partials (FC tail)
+  // inter-layer dataflow (ptx.cuh: wait_images / signal_rows); nullptr = whole-grid dependency (pdl_wait)
+  int* progress;
+  int wait_target;
+  int sig_fence;  // experiments only: 0 drops the release fence before the progress update (UNSAFE)
 };
 
 template <int BLOCK_N>

@@ -34,6 +34,48 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---------------------------------------------------------------- inter-layer dataflow (per-image progress counters)
+// Layer kernels overlap across launch boundaries: instead of waiting for the whole previous grid, a tile waits
+// until every image it reads has been completely written by all earlier layers.  progress[img] counts finished
+// (output row x 32-channel chunk) units cumulatively over the layers of one forward pass; layer L's tiles need
+// progress[img] >= target_L = sum over earlier layers of rows_per_image * Cout / 32.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// Converged warp: block until progress[first..last] >= target, then order the async proxy (TMA) after the acquire.
+__device__ __forceinline__ void wait_images(const int* progress, int first, int last, int target) {
+  const int lane = threadIdx.x & 31;
+  for (int base = first; base <= last; base += 32) {
+    const int i = base + lane;
+    uint32_t spins = 0;
+    while (true) {
+      const bool ok = (i > last) || (ld_acquire_gpu(progress + i) >= target);
+      if (__all_sync(0xffffffffu, ok)) break;
+      __nanosleep(40);
+      if (++spins > (1u << 24)) {
+        printf("frb: dataflow wait timeout block %d image %d target %d\n", blockIdx.x, i, target);
+        __trap();
+      }
+    }
+  }
+  fence_proxy_async_global();
+}
+// Converged warp, after its stores of one tile: lanes with valid rows add `units_per_row` per row to their image.
+__device__ __forceinline__ void signal_rows(int* progress, bool valid, int img, int units_per_row, bool fence = true) {
+  __syncwarp();
+  const unsigned vm = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    const unsigned peers = __match_any_sync(vm, img);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+      if (fence) __threadfence();
+      atomicAdd(progress + img, __popc(peers) * units_per_row);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

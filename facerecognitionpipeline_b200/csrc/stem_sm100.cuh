@@ -24,7 +24,7 @@ constexpr int kStemSmemBytes = 16384 /*A*/ + 8192 /*B*/ + 16384 /*out*/ + (kStem
 __global__ void __launch_bounds__(kStemThreads)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* __restrict__ in,
                const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
-               const float* __restrict__ prelu, int H, int W) {
+               const float* __restrict__ prelu, int H, int W, int* __restrict__ progress) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
@@ -150,7 +150,14 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
       tma_store_commit();
     }
   }
-  if (tid == 0) tma_store_wait<0>();
+  if (tid == 0) {
+    tma_store_wait<0>();  // all rows of this strip are written
+    if (progress != nullptr) {  // inter-layer dataflow: kStemRows x W rows x (64 / 32) chunk units of image `img` are done
+      fence_proxy_async_global();
+      __threadfence();
+      atomicAdd(progress + img, kStemRows * W * 2);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {

@@ -58,3 +58,96 @@ def test_config1_match_single_face_loop(tmp_path):
     # top-k: identical index lists when matching the SAME embeddings (match parity proper is test_gpu_match)
     res, _ = gm.search_batch(ref_emb, 5)
     assert [[r[0] for r in row] for row in res] == [[f"STU{i:04d}" for i in row] for row in eidx]
+
+
+def test_config4_warp_embed_match_stream(ctx):
+    """BASELINE config 4 shape: landmark warp -> IR-101 embed -> match as one device-resident stream.
+    1024 faces warped out of 256x256 frames by `frb_warp_normalize` straight into the NHWC bf16 tensor the
+    backbone reads, embedded and matched against a 100k-row gallery.  Checked through the oracle on the first
+    8 faces (same frames, same landmarks, reference align + preprocess + fp32 forward) and through
+    size-independent properties on all 1024: unit norms, every enrolled face retrieves itself at rank 1 with
+    score ~1, accept == (top-1 score >= thr)."""
+    import ctypes as C
+    import cv2
+    import torch
+    from oracle import align as oa
+    from facerecognitionpipeline_b200 import _native, weights
+    from facerecognitionpipeline_b200.face_recognition import similarity_template, estimate_matrix
+
+    rng = np.random.default_rng(7)
+    B, S = 1024, 112
+    sd = ob.random_state_dict("ir_101", "adaface", seed=3)
+    weights.build_program(sd, "ir_101", "adaface").load_into(ctx)
+    ctx.backbone_token = None
+    tpl = similarity_template(S)
+    frames = np.stack([cv2.GaussianBlur(rng.integers(0, 256, (256, 256, 3), dtype=np.uint8), (0, 0), 2.0) for _ in range(16)])
+    jobs = (_native.WarpJob * B)()
+    lms = []
+    for i in range(B):
+        ang, sc = np.deg2rad(rng.uniform(-20, 20)), rng.uniform(1.5, 2.2)
+        R = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]]) * sc
+        lm = ((tpl - S / 2) @ R.T + np.array([128 + rng.uniform(-8, 8), 128 + rng.uniform(-8, 8)]) + rng.normal(0, 0.5, (5, 2))).astype(np.float32)
+        lms.append(lm)
+        M = estimate_matrix(lm, tpl)
+        jobs[i].src_off, jobs[i].H, jobs[i].W, jobs[i].pitch = (i % 16) * 256 * 256 * 3, 256, 256, 256 * 3
+        for j, v in enumerate(np.asarray(M, np.float64).reshape(6)):
+            jobs[i].M[j] = float(v)
+    dev = torch.device("cuda", 0)
+    d_frames = torch.from_numpy(frames).to(dev)
+    x = torch.empty((B, 112, 112, 3), dtype=torch.bfloat16, device=dev)
+    emb = torch.empty((B, 512), dtype=torch.float32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ctx.frb_warp_normalize(d_frames.data_ptr(), jobs, B, S, None, x.data_ptr(), st)
+    ctx.frb_embed(x.data_ptr(), B, _native.FRB_EMBED_L2 | _native.FRB_EMBED_RENORM, emb.data_ptr(), None, None, st)
+    torch.cuda.synchronize()
+    E = emb.cpu().numpy()
+    assert np.abs(np.linalg.norm(E, axis=1) - 1).max() < 1e-5
+    # oracle on the first 8 faces: the reference's own align + preprocess + fp32 forward
+    crops = [oa.align(frames[i % 16], lms[i], S) for i in range(8)]
+    ref = oe.OracleEmbedder("ir_101", "adaface", state_dict=sd).extract_embeddings_batch(crops)
+    cos = (E[:8] * ref).sum(1) / (np.linalg.norm(E[:8], axis=1) * np.linalg.norm(ref, axis=1))
+    assert cos.min() >= 0.999
+    # gallery: the 1024 embeddings enrolled among 100k random identities; every face must retrieve itself
+    N, thr = 100_000, 0.9
+    g = torch.Generator(device=dev).manual_seed(5)
+    G = torch.randn((N, 512), generator=g, device=dev)
+    G /= G.norm(dim=1, keepdim=True)
+    where = torch.randperm(N, generator=g, device=dev)[:B]
+    G[where] = emb
+    ctx.frb_gallery_upload(G.data_ptr(), N, 0, 1)
+    ctx.gallery_token = None
+    sc = torch.empty((B, 5), dtype=torch.float32, device=dev)
+    ix = torch.empty((B, 5), dtype=torch.int64, device=dev)
+    ac = torch.empty((B,), dtype=torch.uint8, device=dev)
+    ctx.frb_match(emb.data_ptr(), B, 5, thr, 1, sc.data_ptr(), ix.data_ptr(), ac.data_ptr(), None, st)
+    torch.cuda.synchronize()
+    assert torch.equal(ix[:, 0], where)
+    assert (sc[:, 0] - 1).abs().max().item() < 1e-5
+    assert torch.equal(ac.bool(), sc[:, 0] >= thr) and bool(ac.all())
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all())               # sorted descending
+
+
+def test_launch_schedules_are_bit_identical(tmp_path):
+    """The three launch schedules of the backbone — plain stream order (FRB_PDL=0), programmatic dependent
+    launch (default) and per-image dataflow counters (FRB_DATAFLOW=1, layers overlap across launch boundaries)
+    — must produce bit-identical embeddings: they only change WHEN a tile runs, never what it computes."""
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "run.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "from oracle import backbone as ob\n"
+        "from facerecognitionpipeline_b200.face_embedder import FaceEmbedder\n"
+        "rng = np.random.default_rng(11)\n"
+        "crops = [rng.integers(0, 256, (112, 112, 3), dtype=np.uint8) for _ in range(150)]\n"
+        "fe = FaceEmbedder('ir_50', state_dict=ob.random_state_dict('ir_50', 'adaface', seed=2), max_batch=150)\n"
+        "for _ in range(3): e = fe.extract_embeddings_batch(crops)\n"
+        "np.save(sys.argv[1], e)\n")
+    outs = []
+    for name, env in (("plain", {"FRB_PDL": "0"}), ("pdl", {}), ("dataflow", {"FRB_DATAFLOW": "1"})):
+        out = tmp_path / f"{name}.npy"
+        subprocess.run([sys.executable, str(script), str(out)], check=True, env={**os.environ, **env}, timeout=600)
+        outs.append(np.load(out))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
