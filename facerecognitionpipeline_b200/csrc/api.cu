@@ -54,6 +54,7 @@ struct frb_ctx {
   int conv_mode = 2;  // 2 = CTA-pair kernel, 1 = 1-CTA kernel with weight multicast
   int use_slab = 1;   // activation-slab kernel for eligible 3x3 stride-1 layers (FRB_SLAB=0 disables)
   int use_pdl = 1;    // programmatic dependent launch between backbone kernels (FRB_PDL=0 disables)
+  int match_pair = 1;   // CTA-pair match filter for P > 128 (FRB_MATCH_PAIR=0 disables)
   int use_dataflow = 0;  // per-image progress counters instead of whole-grid dependencies (FRB_DATAFLOW=0 disables; needs PDL)
   int* d_progress = nullptr;
   int progress_cap = 0;
@@ -85,6 +86,7 @@ struct frb_ctx {
   long long gal_N = 0, gal_first = 0, gal_cap = 0;
   float* d_gal_maxnorm = nullptr;
   CUtensorMap tmG;
+  CUtensorMap tmG2;  // same gallery, 128-row box (CTA-pair match kernel)
 
   // match workspace
   float* d_probe_f32 = nullptr;
@@ -458,6 +460,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_SLAB")) ctx->use_slab = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
   if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
+  if (const char* e = getenv("FRB_MATCH_PAIR")) ctx->match_pair = atoi(e);
   if (!ctx->use_pdl) ctx->use_dataflow = 0;
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
@@ -887,6 +890,7 @@ extern "C" int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, lon
   ctx->launches++;
   CK(cudaDeviceSynchronize());
   if (make_tmap_2d(ctx, &ctx->tmG, ctx->d_gal_bf16, 512, static_cast<uint64_t>(N), kMatchBN)) return 1;
+  if (make_tmap_2d(ctx, &ctx->tmG2, ctx->d_gal_bf16, 512, static_cast<uint64_t>(N), kMatchBN / 2)) return 1;
   return 0;
 }
 
@@ -978,25 +982,28 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
   MatchParams mp;
   mp.P = P;
   mp.N = N;
-  mp.p_tiles = (P + 127) / 128;
+  const bool pair_mode = P > 128 && ctx->match_pair;   // two probe tiles per CTA pair (match_filter2_kernel)
+  const int units = pair_mode ? ctx->num_sms / 2 : ctx->num_sms;  // concurrently running work items
+  mp.p_tiles = pair_mode ? (P + 255) / 256 : (P + 127) / 128;
   mp.g_tiles = static_cast<int>((N + kMatchBN - 1) / kMatchBN);
   // Slices: long enough that the per-row top-k lists settle (few insertions => cheap epilogue), and
-  // p_tiles * slices close to a multiple of the SM count (whole waves).  cost ~ waves * tiles-per-slice.
+  // p_tiles * slices close to a multiple of the number of concurrent work items (whole waves).
   {
-    const int smin = std::max(1, (ctx->num_sms + mp.p_tiles - 1) / mp.p_tiles);
+    const int smin = std::max(1, (units + mp.p_tiles - 1) / mp.p_tiles);
     const int smax = std::max(1, std::min(std::min(mp.g_tiles, kMaxCandPad / kCand), smin * 8));
     long best_cost = -1;
     int best_s = 1;
     for (int sl = std::min(smin, smax); sl <= smax; ++sl) {
       const int tps = (mp.g_tiles + sl - 1) / sl;
       const int real = (mp.g_tiles + tps - 1) / tps;
-      const long waves = (static_cast<long>(mp.p_tiles) * real + ctx->num_sms - 1) / ctx->num_sms;
+      const long waves = (static_cast<long>(mp.p_tiles) * real + units - 1) / units;
       const long cost = waves * (tps + 2);
       if (best_cost < 0 || cost < best_cost) {
         best_cost = cost;
         best_s = real;
       }
     }
+    if (const char* e = getenv("FRB_MATCH_SLICES")) best_s = std::max(1, std::min(atoi(e), smax));
     mp.tiles_per_slice = (mp.g_tiles + best_s - 1) / best_s;
     mp.slices = (mp.g_tiles + mp.tiles_per_slice - 1) / mp.tiles_per_slice;
   }
@@ -1013,13 +1020,31 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
   mp.cand_idx = ctx->d_cand_idx;
   CUtensorMap tmP;
   if (make_tmap_2d(ctx, &tmP, ctx->d_probe_bf16, 512, static_cast<uint64_t>(P), 128)) return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(match_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MatchSmem::kTotal));
-    attr_set = true;
+  if (pair_mode) {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      CK(cudaFuncSetAttribute(match_filter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Match2Smem::kTotal));
+      attr2_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(std::min(mp.p_tiles * mp.slices, units) * 2);
+    cfg.blockDim = dim3(kMatch2Threads);
+    cfg.dynamicSmemBytes = Match2Smem::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    fill_launch_attrs(attr, 2);
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, match_filter2_kernel, tmP, ctx->tmG2, mp));
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CK(cudaFuncSetAttribute(match_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MatchSmem::kTotal));
+      attr_set = true;
+    }
+    const int grid = std::min(mp.p_tiles * mp.slices, ctx->num_sms);
+    match_filter_kernel<<<grid, kMatchThreads, MatchSmem::kTotal, st>>>(tmP, ctx->tmG, mp);
   }
-  const int grid = std::min(mp.p_tiles * mp.slices, ctx->num_sms);
-  match_filter_kernel<<<grid, kMatchThreads, MatchSmem::kTotal, st>>>(tmP, ctx->tmG, mp);
   CK(cudaGetLastError());
   ctx->launches++;
   FinalizeParams fp;

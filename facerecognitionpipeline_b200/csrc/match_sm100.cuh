@@ -13,7 +13,7 @@
 // asc) and proves, per row, that the bf16 filter cannot have dropped a true top-k entry
 // (rows failing the proof are re-done by the exact scan).
 #pragma once
-#include "ptx.cuh"
+#include "gemm2_sm100.cuh"
 
 namespace frb {
 
@@ -51,6 +51,35 @@ __device__ __forceinline__ void cand_insert(float (&ls)[kCand], int (&li)[kCand]
       const float ts = ls[i]; ls[i] = ls[i - 1]; ls[i - 1] = ts;
       const int ti = li[i]; li[i] = li[i - 1]; li[i - 1] = ti;
     }
+  }
+}
+
+// Fold 32 consecutive scores into the row's running top-kCand.  The common case (nothing beats the current
+// kCand-th score) costs one max-reduction.  Otherwise candidates are taken one at a time in (score desc, column asc)
+// order — argmax, insert, knock out, repeat — so a warp in which a single lane has a single candidate pays ~150
+// instructions, not 32 predicated insertions (~1300): with 32 independent rows per warp SOME lane has a
+// candidate in most chunks until ~10^5 scores have been seen, and that path bounded the whole match
+// (profiles/r01c: tensor pipe 37 % active at P = 4096).
+__device__ __forceinline__ void cand_scan32(float (&ls)[kCand], int (&li)[kCand], float (&v)[32], int base) {
+  float m = v[0];
+#pragma unroll
+  for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+  if (!(m > ls[kCand - 1])) return;
+#pragma unroll 1
+  while (true) {
+    float best = v[0];
+    int bj = 0;
+#pragma unroll
+    for (int j = 1; j < 32; ++j)
+      if (v[j] > best) {  // strict: the lowest column wins a tie
+        best = v[j];
+        bj = j;
+      }
+    if (!(best > ls[kCand - 1])) break;
+    cand_insert(ls, li, best, base + bj);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == bj) v[j] = -INFINITY;
   }
 }
 
@@ -220,15 +249,7 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
             for (int j = 0; j < 32; ++j)
               v[j] = (c * 32 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY;
           }
-          float m = v[0];
-#pragma unroll
-          for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-          if (m > ls[kCand - 1]) {
-            const int base = static_cast<int>(col0) + c * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (v[j] > ls[kCand - 1]) cand_insert(ls, li, v[j], base + j);
-          }
+          cand_scan32(ls, li, v, static_cast<int>(col0) + c * 32);
         }
         tc_fence_before();
         __syncwarp();
@@ -256,6 +277,227 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2), used when there are at least two probe tiles (P > 128).
+// A pair works on TWO probe tiles (256 probes) against the same gallery slice: each CTA keeps its own 128-probe
+// tile resident and streams only HALF of every gallery tile (128 of 256 rows per K block); the tensor cores
+// exchange the halves.  That halves the L2->SM gallery traffic per probe — the bound of the 1-CTA kernel
+// (64 B/clk/SM needed against the ~42 B/clk/SM ingest ceiling) — and doubles the ring depth (6 x 16 KB).
+constexpr int kMatch2BStages = 6;
+constexpr int kMatch2Threads = 192;
+
+struct Match2Smem {
+  static constexpr int kABytes = 128 * 64 * 2;              // one K block of this CTA's probe tile
+  static constexpr int kBBytes = (kMatchBN / 2) * 64 * 2;   // this CTA's half of a gallery tile K block (16 KB)
+  static constexpr int kTotal = kMatchKB * kABytes + kMatch2BStages * kBBytes + 256 + 1024;
+};
+
+// p.p_tiles here = number of probe-tile PAIRS; tmG2: gallery map with a 128-row box.
+__global__ void __launch_bounds__(kMatch2Threads, 1)
+match_filter2_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmG2,
+                     const MatchParams p) {
+  using S = Match2Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kMatchKB * S::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kMatch2BStages * S::kBBytes);
+  uint64_t* a_full = bars;                      // leader only
+  uint64_t* a_empty = bars + 1;                 // per CTA (commit multicast)
+  uint64_t* b_full = bars + 2;                  // [6] leader only
+  uint64_t* b_empty = b_full + kMatch2BStages;  // [6] per CTA
+  uint64_t* t_full = b_empty + kMatch2BStages;  // [2] per CTA
+  uint64_t* t_empty = t_full + 2;               // [2] leader only, 8 arrivals
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(cluster_ctarank());
+  const bool leader = (crank == 0);
+  const int total_items = p.p_tiles * p.slices;
+  const int first_item = blockIdx.x >> 1, item_step = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmP);
+    prefetch_tmap(&tmG2);
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int i = 0; i < kMatch2BStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem2_alloc(tmem_ptr_smem, 512);
+    tmem2_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+
+  if (warp == 0) {
+    // ---- TMA producer (both CTAs): own probe tile + own half of every gallery tile, completing on the leader's barriers
+    const uint32_t a_full_leader = mapa_u32(smem_u32(a_full), 0);
+    const uint32_t b_full_leader0 = mapa_u32(smem_u32(&b_full[0]), 0);
+    int stage = 0;
+    uint32_t phase = 0, a_phase = 0;
+    for (int item = first_item; item < total_items; item += item_step) {
+      const int pt = (item % p.p_tiles) * 2 + crank;
+      const int gs = item / p.p_tiles;
+      const int t_begin = gs * p.tiles_per_slice;
+      const int t_end = min(p.g_tiles, t_begin + p.tiles_per_slice);
+      mbar_wait(a_empty, a_phase ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_arrive_expect_tx(a_full, 2 * kMatchKB * S::kABytes);
+#pragma unroll
+        for (int kb = 0; kb < kMatchKB; ++kb) tma2_load_2d(&tmP, a_full_leader, smem_a + kb * S::kABytes, kb * 64, pt * 128);
+      }
+      __syncwarp();
+      a_phase ^= 1;
+      for (int t = t_begin; t < t_end; ++t) {
+#pragma unroll 1
+        for (int kb = 0; kb < kMatchKB; ++kb) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * S::kBBytes);
+            tma2_load_2d(&tmG2, b_full_leader0 + 8 * stage, smem_b + stage * S::kBBytes, kb * 64,
+                         t * kMatchBN + crank * (kMatchBN / 2));
+          }
+          __syncwarp();
+          if (++stage == kMatch2BStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (leader): 256 probes x 256 gallery rows per tile
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, kMatchBN);
+      const uint64_t desc0 = umma_desc_sw128(0);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | static_cast<uint32_t>(desc0);
+      const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | static_cast<uint32_t>(desc0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+      for (int item = first_item; item < total_items; item += item_step) {
+        const int gs = item / p.p_tiles;
+        const int t_begin = gs * p.tiles_per_slice;
+        const int t_end = min(p.g_tiles, t_begin + p.tiles_per_slice);
+        mbar_wait(a_full, a_phase);
+        a_phase ^= 1;
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(&t_empty[acc], acc_phase ^ 1);
+          const uint32_t tmem_d = tmem_base + acc * kMatchBN;
+#pragma unroll 1
+          for (int kb = 0; kb < kMatchKB; ++kb) {
+            mbar_wait(&b_full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + kb * (S::kABytes >> 4);
+            const uint32_t b_lo = b_lo0 + stage * (S::kBBytes >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma2_bf16_ss_lo(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma2_commit_pair(&b_empty[stage]);
+              if (kb == kMatchKB - 1) {
+                umma2_commit_pair(&t_full[acc]);
+                if (t == t_end - 1) umma2_commit_pair(a_empty);
+              }
+            }
+            __syncwarp();
+            if (++stage == kMatch2BStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ---- epilogue (both CTAs): one probe row per thread, running top-kCand of the slice in registers
+    const int quad = warp & 3;
+    const uint32_t t_empty_leader0 = mapa_u32(smem_u32(&t_empty[0]), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = first_item; item < total_items; item += item_step) {
+      const int pt = (item % p.p_tiles) * 2 + crank;
+      const int gs = item / p.p_tiles;
+      const int t_begin = gs * p.tiles_per_slice;
+      const int t_end = min(p.g_tiles, t_begin + p.tiles_per_slice);
+      const int row = pt * 128 + quad * 32 + lane;
+      float ls[kCand];
+      int li[kCand];
+#pragma unroll
+      for (int i = 0; i < kCand; ++i) {
+        ls[i] = -INFINITY;
+        li[i] = -1;
+      }
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&t_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kMatchBN;
+        const long long col0 = static_cast<long long>(t) * kMatchBN;
+        const int ncols = static_cast<int>(min(static_cast<long long>(kMatchBN), p.N - col0));
+#pragma unroll 1
+        for (int c = 0; c < kMatchBN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (c * 32 >= ncols) continue;
+          float v[32];
+          if (ncols == kMatchBN) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (c * 32 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY;
+          }
+          cand_scan32(ls, li, v, static_cast<int>(col0) + c * 32);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(t_empty_leader0 + 8 * acc);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (row < p.P) {
+        const size_t o = (static_cast<size_t>(row) * p.slices + gs) * kCand;
+        float4* ds = reinterpret_cast<float4*>(p.cand_score + o);
+        int4* di = reinterpret_cast<int4*>(p.cand_idx + o);
+        ds[0] = make_float4(ls[0], ls[1], ls[2], ls[3]);
+        ds[1] = make_float4(ls[4], ls[5], ls[6], ls[7]);
+        di[0] = make_int4(li[0], li[1], li[2], li[3]);
+        di[1] = make_int4(li[4], li[5], li[6], li[7]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem2_dealloc(tmem_base, 512);
   }
 }
 

@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Match-only timing on one GPU: P probes x N x 512 gallery, top-5 (BASELINE config 3 per-GPU shape when N = 1M / world)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from facerecognitionpipeline_b200 import _native
+ctx = _native.Context(0)
+dev = torch.device("cuda", 0)
+N = int(os.environ.get("FRB_N", 1_000_000))
+g = torch.Generator(device=dev).manual_seed(7)
+G = torch.randn((N, 512), generator=g, device=dev); G /= G.norm(dim=1, keepdim=True)
+ctx.frb_gallery_upload(G.data_ptr(), N, 0, 1)
+st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+for P in [int(a) for a in sys.argv[1:]] or [256, 1024, 4096]:
+    probes = G[torch.randint(0, N, (P,), generator=g, device=dev)] + 0.03 * torch.randn((P, 512), generator=g, device=dev)
+    probes[::7] = torch.randn((probes[::7].shape[0], 512), generator=g, device=dev)
+    sc = torch.empty((P, 5), dtype=torch.float32, device=dev); ix = torch.empty((P, 5), dtype=torch.int64, device=dev)
+    ac = torch.empty((P,), dtype=torch.uint8, device=dev)
+    f = lambda: ctx.frb_match(probes.data_ptr(), P, 5, 0.35, 1, sc.data_ptr(), ix.data_ptr(), ac.data_ptr(), None, st)
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10): f()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    print(f"P={P:5d} N={N}: {ms:8.3f} ms  {P*1024.0*N/ms/1e9:7.1f} TFLOP/s  gallery pass {N*1024/ms/1e6:7.1f} GB/s-equivalent  flagged {ctx._lib.frb_match_last_flagged(ctx.handle)}", flush=True)
