@@ -894,6 +894,21 @@ extern "C" int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, lon
   return 0;
 }
 
+// Batched enrollment aggregation: templates of S identities from their embeddings, on the device.
+extern "C" int frb_aggregate_templates(frb_ctx* ctx, const float* d_emb, const long long* d_seg, int S, int max_rows,
+                                       int method, float min_similarity, float* d_templates, int* d_kept, void* stream) {
+  if (!ctx) return 1;
+  if (S <= 0) return 0;
+  if (method < 0 || method > 2) return fail(ctx, "frb_aggregate_templates: method must be 0 (mean), 1 (median) or 2 (weighted_mean)");
+  if (max_rows > kAggMaxRows) return fail(ctx, "frb_aggregate_templates: at most %d embeddings per identity (got %d)", kAggMaxRows, max_rows);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  aggregate_templates_kernel<<<S, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_emb, d_seg, method, min_similarity, d_templates, d_kept);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
 extern "C" long long frb_gallery_size(frb_ctx* ctx) { return ctx ? ctx->gal_N : 0; }
 extern "C" int frb_match_last_flagged(frb_ctx* ctx) { return ctx ? ctx->last_flagged : 0; }
 

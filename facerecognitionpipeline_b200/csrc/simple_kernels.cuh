@@ -268,6 +268,130 @@ flip_fuse_kernel(const float* __restrict__ emb2, int B, float* __restrict__ out,
   }
 }
 
+// ------------------------------------------------------------------ enrollment template aggregation
+// GalleryManager._aggregate_embeddings + _filter_quality_embeddings (reference gallery_manager.py:104-122,297-317),
+// batched over identities: one block per identity, its n embeddings are rows [seg[s], seg[s+1]) of `emb`.
+//   n == 1 : template = the row itself (NOT re-normalised, :298-299)
+//   n  > 2 : quality filter - gram matrix, diagonal zeroed, row mean over ALL n columns (divides by n, :110-112), keep
+//            rows with mean >= min_sim, fall back to the two best rows when fewer than two survive (:117-119)
+//   then mean (method 0) / median (1) / weighted mean (2: weights = gram row means of the KEPT rows incl. the
+//   diagonal, normalised to sum 1) over the kept rows in their original order, and v / (||v|| + 1e-8).
+// n <= kAggMaxRows.  fp32 throughout like the reference; BLAS summation order is not reproduced (1e-6 agreement).
+constexpr int kAggMaxRows = 64;
+
+__global__ void __launch_bounds__(128)
+aggregate_templates_kernel(const float* __restrict__ emb, const long long* __restrict__ seg, int method, float min_sim,
+                           float* __restrict__ out, int* __restrict__ out_kept) {
+  __shared__ float gram[kAggMaxRows][kAggMaxRows + 1];
+  __shared__ float row_score[kAggMaxRows];
+  __shared__ float weight[kAggMaxRows];
+  __shared__ int kept_idx[kAggMaxRows];
+  __shared__ int n_kept_s;
+  __shared__ float red[4];
+  const int s = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const long long r0 = seg[s];
+  const int n = static_cast<int>(seg[s + 1] - r0);
+  const float* E = emb + r0 * 512;
+  float* o = out + static_cast<size_t>(s) * 512;
+  if (n <= 0) {
+    for (int d = t; d < 512; d += 128) o[d] = 0.f;
+    if (t == 0 && out_kept) out_kept[s] = 0;
+    return;
+  }
+  if (n == 1) {
+    for (int d = t; d < 512; d += 128) o[d] = E[d];
+    if (t == 0 && out_kept) out_kept[s] = 1;
+    return;
+  }
+  // gram matrix: one warp per (i, j >= i) pair
+  for (int pidx = warp; pidx < n * n; pidx += 4) {
+    const int i = pidx / n, j = pidx - i * n;
+    if (j < i) continue;
+    float acc = 0.f;
+    for (int d = lane; d < 512; d += 32) acc = fmaf(E[i * 512 + d], E[j * 512 + d], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      gram[i][j] = acc;
+      gram[j][i] = acc;
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    int nk = 0;
+    if (n <= 2) {
+      for (int i = 0; i < n; ++i) kept_idx[nk++] = i;
+    } else {
+      for (int i = 0; i < n; ++i) {
+        float sum = 0.f;
+        for (int j = 0; j < n; ++j)
+          if (j != i) sum += gram[i][j];
+        row_score[i] = __fdiv_rn(sum, static_cast<float>(n));
+        if (row_score[i] >= min_sim) kept_idx[nk++] = i;
+      }
+      if (nk < 2) {  // the two best rows (np.argsort(avg)[-2:]: second best first)
+        int b1 = 0;
+        for (int i = 1; i < n; ++i)
+          if (row_score[i] >= row_score[b1]) b1 = i;
+        int b2 = (b1 == 0) ? 1 : 0;
+        for (int i = 0; i < n; ++i)
+          if (i != b1 && row_score[i] >= row_score[b2]) b2 = i;
+        kept_idx[0] = b2;
+        kept_idx[1] = b1;
+        nk = 2;
+      }
+    }
+    n_kept_s = nk;
+    if (method == 2) {  // weights from the gram of the kept rows (diagonal included), normalised to sum 1
+      float wsum = 0.f;
+      for (int a = 0; a < nk; ++a) {
+        float sum = 0.f;
+        for (int b = 0; b < nk; ++b) sum += gram[kept_idx[a]][kept_idx[b]];
+        weight[a] = __fdiv_rn(sum, static_cast<float>(nk));
+        wsum += weight[a];
+      }
+      for (int a = 0; a < nk; ++a) weight[a] = __fdiv_rn(weight[a], wsum);
+    }
+    if (out_kept) out_kept[s] = nk;
+  }
+  __syncthreads();
+  const int nk = n_kept_s;
+  float v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int d = t + 128 * q;
+    if (method == 1) {  // median over the kept rows: insertion sort of <= 64 values
+      float buf[kAggMaxRows];
+      for (int a = 0; a < nk; ++a) {
+        const float x = E[kept_idx[a] * 512 + d];
+        int b = a;
+        while (b > 0 && buf[b - 1] > x) {
+          buf[b] = buf[b - 1];
+          --b;
+        }
+        buf[b] = x;
+      }
+      v[q] = (nk & 1) ? buf[nk >> 1] : 0.5f * (buf[(nk >> 1) - 1] + buf[nk >> 1]);
+    } else if (method == 2) {
+      float acc = 0.f;
+      for (int a = 0; a < nk; ++a) acc += E[kept_idx[a] * 512 + d] * weight[a];
+      v[q] = acc;
+    } else {
+      float acc = 0.f;
+      for (int a = 0; a < nk; ++a) acc += E[kept_idx[a] * 512 + d];
+      v[q] = __fdiv_rn(acc, static_cast<float>(nk));
+    }
+  }
+  float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  const float nrm = __fsqrt_rn(red[0] + red[1] + red[2] + red[3]) + 1e-8f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) o[t + 128 * q] = __fdiv_rn(v[q], nrm);
+}
+
 // ------------------------------------------------------------------ probe / gallery prep
 // q = q / (||q|| + 1e-8)  (GalleryManager.search, gallery_manager.py:195), fp32, + bf16 copy
 __global__ void __launch_bounds__(128)

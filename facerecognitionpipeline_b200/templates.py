@@ -73,3 +73,47 @@ def drop_outliers(embeddings: np.ndarray, threshold: float = 0.7) -> np.ndarray:
         return embeddings
     row_score = (embeddings @ embeddings.T).mean(axis=1)
     return embeddings[row_score >= np.median(row_score) * threshold]
+
+
+# ---------------------------------------------------------------------------------------------------
+# Device version for bulk gallery builds: embeddings stay in HBM between frb_embed,
+# aggregation and frb_gallery_upload.  GalleryManager.add_student keeps using the numpy functions above
+# (they are the reference's arithmetic to the bit); this path agrees with them to ~1e-6.
+METHOD_CODES = {"mean": 0, "median": 1, "weighted_mean": 2}
+DEVICE_MAX_ROWS = 64
+
+
+def aggregate_on_device(embeddings, counts, method: str = "mean", min_similarity: float = QUALITY_MIN_SIMILARITY,
+                        device: int = 0, upload_as_gallery: bool = False, first_global_id: int = 0):
+    """Templates of S identities in one kernel launch.
+
+    embeddings: [T, 512] float32, a CUDA torch tensor (used in place) or a numpy array (copied once);
+    counts: rows per identity, in order (sum == T, each <= 64).  Unknown methods fall back to mean like
+    GalleryManager does.  Returns (templates [S,512] CUDA tensor, kept [S] CUDA int32 tensor); with
+    upload_as_gallery the templates also become the context's resident gallery without leaving the device."""
+    import ctypes as C
+
+    import torch
+
+    from . import _native
+    ctx = _native.default_context(device)
+    dev = torch.device("cuda", device)
+    emb = embeddings if isinstance(embeddings, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(embeddings, dtype=np.float32))
+    emb = emb.to(dev, dtype=torch.float32).contiguous().reshape(-1, 512)
+    counts = np.asarray(counts, dtype=np.int64)
+    if counts.sum() != emb.shape[0]:
+        raise ValueError("counts do not add up to the number of embedding rows")
+    if len(counts) and counts.max() > DEVICE_MAX_ROWS:
+        raise ValueError(f"at most {DEVICE_MAX_ROWS} embeddings per identity on the device path")
+    S = len(counts)
+    seg = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)).to(dev)
+    out = torch.empty((S, 512), dtype=torch.float32, device=dev)
+    kept = torch.empty((S,), dtype=torch.int32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ctx.frb_aggregate_templates(emb.data_ptr(), seg.data_ptr(), S, int(counts.max()) if S else 0, METHOD_CODES.get(method, 0),
+                                float(min_similarity), out.data_ptr(), kept.data_ptr(), st)
+    if upload_as_gallery and S:
+        torch.cuda.current_stream(dev).synchronize()
+        ctx.frb_gallery_upload(out.data_ptr(), S, int(first_global_id), 1)
+        ctx.gallery_token = None
+    return out, kept

@@ -98,6 +98,13 @@ int frb_embed_profile(frb_ctx* ctx, const void* d_in, int B, int flags, float* d
  * first_global_id is added to local row numbers in every result (identity-sharded galleries). */
 int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, long long first_global_id, int is_device);
 long long frb_gallery_size(frb_ctx* ctx);
+/* Enrollment aggregation for S identities at once (GalleryManager._aggregate_embeddings incl. the quality filter,
+ * gallery_manager.py:104-122,297-317): identity s owns rows [d_seg[s], d_seg[s+1]) of d_emb [T][512] f32 (device;
+ * d_seg is S+1 int64 on the device; at most max_rows <= 64 rows each).  method: 0 mean, 1 median, 2 weighted_mean.
+ * Outputs (device): d_templates [S][512] f32 (ready for frb_gallery_upload(is_device=1)), d_kept [S] rows that
+ * survived the quality filter (may be NULL). */
+int frb_aggregate_templates(frb_ctx* ctx, const float* d_emb, const long long* d_seg, int S, int max_rows, int method,
+                            float min_similarity, float* d_templates, int* d_kept, void* stream);
 /* d_probes: [P][512] f32.  normalize != 0 applies q/(||q||+1e-8) first (search()).
  * Outputs (device): scores f32 [P][k], idx i64 [P][k] (global ids, -1 = fewer than k rows),
  * accept u8 [P] (top-1 score >= thr), scores64 f64 [P][k] (optional, for cross-rank merge). */
