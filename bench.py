@@ -39,80 +39,116 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clock / throttle reasons during the timed region: NVML polled every 5 ms from a thread (the timed
+    region of a default run is only ~0.15 s, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.sm, self.power, self.mx, self.reasons, self.src = gpu_index, [], [], None, set(), None
+        self._stop = threading.Event()
+        self.t = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for name, bit in bits.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                        self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.src = "nvml"
+            self.t = threading.Thread(target=poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.src = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
+    def _smi_once(self):
         try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-            except ValueError:
-                continue
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                  str(self._physical_index())], capture_output=True, text=True, timeout=10).stdout
+            f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+            self.sm.append(float(f[1]))
+            self.mx = float(f[2])
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+                    self.reasons.add(name)
+            self.src = "nvidia-smi"
+        except Exception:
+            pass
+
+    def stop(self):
+        """Call while the GPU is still busy with the last timed step (before the closing synchronize)."""
+        if self.t is None or not self.sm:
+            self._smi_once()
+        self._stop.set()
+        if self.t is not None:
+            self.t.join(timeout=1)
+        if not self.sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["clock query unavailable"], samples=0)
+        return dict(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.mx, reasons=sorted(self.reasons),
+                    samples=len(self.sm), power_w_max=max(self.power) if self.power else None, source=self.src)
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n_faces, n_probes, gallery_rows, seed=0, threads=None):
+class CpuReference:
     """The reference's CPU path on this box's host cores: torch-eager fp32 IR-101 in batches of 32
     (face_embedder.py:137-182, via the oracle restatement) + numpy matching exactly as
     GalleryManager.search does per probe with the matrix cached (gallery_manager.py:195-197).
-    Returns seconds per face for both halves."""
-    import torch
-    from oracle import backbone, embedder
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    rng = np.random.default_rng(seed)
-    sd = backbone.random_state_dict("ir_101", "adaface", seed, calibrate=False)
-    emb = embedder.OracleEmbedder("ir_101", "adaface", state_dict=sd)
-    crops = [rng.integers(0, 256, (112, 112, 3), dtype=np.uint8) for _ in range(n_faces)]
-    emb.extract_embeddings_batch(crops[:2])  # warm-up
-    t0 = time.perf_counter()
-    E = emb.extract_embeddings_batch(crops, normalize=True, batch_size=32)
-    t_embed = (time.perf_counter() - t0) / n_faces
-    G = rng.standard_normal((gallery_rows, 512), dtype=np.float32)
-    G /= np.linalg.norm(G, axis=1, keepdims=True)
-    t0 = time.perf_counter()
-    for i in range(n_probes):
-        q = E[i % len(E)]
-        q = q / (np.linalg.norm(q) + 1e-8)
-        s = np.dot(G, q)
-        _ = np.argsort(s)[::-1][:5]
-    t_match = (time.perf_counter() - t0) / n_probes
-    return t_embed, t_match, threads
+    Model and gallery are built once; `sample` times one bounded sample and returns seconds per face / per probe."""
+
+    def __init__(self, gallery_rows, seed=0, threads=None):
+        import torch
+        from oracle import backbone, embedder
+        self.threads = threads or os.cpu_count()
+        torch.set_num_threads(self.threads)
+        self.rng = np.random.default_rng(seed)
+        sd = backbone.random_state_dict("ir_101", "adaface", seed, calibrate=False)
+        self.emb = embedder.OracleEmbedder("ir_101", "adaface", state_dict=sd)
+        G = self.rng.standard_normal((gallery_rows, 512), dtype=np.float32)
+        G /= np.linalg.norm(G, axis=1, keepdims=True)
+        self.G = G
+        self.emb.extract_embeddings_batch([self.rng.integers(0, 256, (112, 112, 3), dtype=np.uint8) for _ in range(2)])
+
+    def sample(self, n_faces, n_probes):
+        crops = [self.rng.integers(0, 256, (112, 112, 3), dtype=np.uint8) for _ in range(n_faces)]
+        t0 = time.perf_counter()
+        E = self.emb.extract_embeddings_batch(crops, normalize=True, batch_size=32)
+        t_embed = (time.perf_counter() - t0) / n_faces
+        t0 = time.perf_counter()
+        for i in range(n_probes):
+            q = E[i % len(E)]
+            q = q / (np.linalg.norm(q) + 1e-8)
+            s = np.dot(self.G, q)
+            _ = np.argsort(s)[::-1][:5]
+        t_match = (time.perf_counter() - t0) / n_probes
+        return t_embed, t_match
 
 
 def run_reference(args):
@@ -122,17 +158,19 @@ def run_reference(args):
     if rank != 0:
         return
     gallery_rows = args.gallery
-    n_faces, n_probes = 16, 4
+    ref = CpuReference(gallery_rows)
+    n_faces, n_probes = 32, 4
     per_step = []
-    threads = os.cpu_count()
+    t_begin = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        te, tm, threads = cpu_reference_sample(n_faces, n_probes, gallery_rows, seed=i)
+        te, tm = ref.sample(n_faces, n_probes)
         if i >= args.warmup:
             per_step.append(te + tm)
-        if i == 0 and (te * n_faces + tm * n_probes) * (args.warmup + args.steps) > 600:
-            n_faces, n_probes = 8, 2
+        if i == 0 and (time.perf_counter() - t_begin) * (args.warmup + args.steps) > 240:
+            n_faces, n_probes = 8, 2              # slow host: keep the whole run within a few minutes
     sec_per_face = float(np.mean(per_step))
     value = 1.0 / sec_per_face
+    threads = ref.threads
     sample = (f"per step: {n_faces} faces torch-eager fp32 IR-101 (batch 32) + {n_probes} probes numpy dot+argsort vs "
               f"{gallery_rows} x 512 f32 (matrix cached); faces/s = 1 / (embed s/face + match s/probe)")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
@@ -238,12 +276,13 @@ def run_ours(args):
         c.record(stream)
         seg.append((a, b, c))
     e_end.record(stream)
+    e_end.synchronize()
+    clocks = sampler.stop()
     barrier()
     launches = ctx.launch_count() - launches0
     ms_total = max_over_ranks(e_start.elapsed_time(e_end))
     embed_ms = float(np.mean([a.elapsed_time(b) for a, b, c in seg]))
     match_ms = float(np.mean([b.elapsed_time(c) for a, b, c in seg]))
-    clocks = sampler.stop()
     value = world * B * K / (ms_total / 1e3)
 
     # ---- end-to-end through the host-buffer C ABI (e2e)
@@ -303,9 +342,11 @@ def run_ours(args):
                          f"inside the timed steps, programmatic dependent launch on); match section {match_ms:.3f} ms/step")
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        te, tm, threads = cpu_reference_sample(32, 8, N)
+        ref = CpuReference(N)
+        te, tm = ref.sample(64, 8)
+        threads = ref.threads
         cpu = dict(value=1.0 / (te + tm), unit=UNIT, cores=threads, kind="port",
-                   sample=f"32 faces torch-eager fp32 IR-101 (batch 32, {te * 1e3:.1f} ms/face) + 8 probes numpy "
+                   sample=f"64 faces torch-eager fp32 IR-101 (batch 32, {te * 1e3:.1f} ms/face) + 8 probes numpy "
                           f"dot+argsort vs {N} x 512 f32 with the matrix cached ({tm * 1e3:.1f} ms/probe)")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",

@@ -64,6 +64,9 @@ SIGNATURES = {
     "frb_backbone_flops_per_face": (C.c_double, [_vp]),
     "frb_gallery_upload": (_i, [_vp, _vp, _ll, _ll, _i]),
     "frb_gallery_size": (_ll, [_vp]),
+    "frb_gallery_upload_samples": (_i, [_vp, _vp, _ll, _vp, _ll, _i]),
+    "frb_identity_scores": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "frb_match_identities": (_i, [_vp, _vp, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "frb_aggregate_templates": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "frb_match": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "frb_match_last_flagged": (_i, [_vp]),

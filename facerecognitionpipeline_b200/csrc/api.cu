@@ -87,6 +87,11 @@ struct frb_ctx {
   float* d_gal_maxnorm = nullptr;
   CUtensorMap tmG;
   CUtensorMap tmG2;  // same gallery, 128-row box (CTA-pair match kernel)
+  // sample gallery (per-identity matching): identity i owns gallery rows [seg[i], seg[i+1])
+  long long* d_seg = nullptr; int* d_sample_identity = nullptr; long long gal_S = 0; size_t seg_cap = 0, sid_cap = 0;
+  long long* d_id_top_idx = nullptr; double* d_id_top_sc = nullptr; unsigned char* d_id_acc = nullptr; float* d_id_sc32 = nullptr;
+  size_t id_top_cap = 0, id_top_sc_cap = 0, id_acc_cap = 0, id_sc32_cap = 0;
+  double* d_id_scores = nullptr; size_t id_scores_elems = 0;
 
   // match workspace
   float* d_probe_f32 = nullptr;
@@ -526,7 +531,8 @@ extern "C" void frb_ctx_destroy(frb_ctx* ctx) {
                   ctx->d_gal_maxnorm, ctx->d_probe_f32, ctx->d_probe_bf16, ctx->d_cand_score, ctx->d_cand_idx,
                   ctx->d_flagged, ctx->d_flag_rows, ctx->d_exact, ctx->d_scores64_tmp, ctx->d_stage_u8,
                   ctx->d_stage_in, ctx->d_stage_emb, ctx->d_stage_norm, ctx->d_stage_sc, ctx->d_stage_idx,
-                  ctx->d_stage_acc, ctx->d_jobs, ctx->d_progress};
+                  ctx->d_stage_acc, ctx->d_jobs, ctx->d_progress, ctx->d_seg, ctx->d_sample_identity, ctx->d_id_top_idx,
+                  ctx->d_id_top_sc, ctx->d_id_acc, ctx->d_id_sc32, ctx->d_id_scores};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto* b : ctx->d_bufs)
@@ -881,6 +887,7 @@ extern "C" int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, lon
     ctx->gal_cap = cap;
   }
   ctx->gal_N = N;
+  ctx->gal_S = 0;  // a plain template gallery: per-identity queries need frb_gallery_upload_samples
   ctx->gal_first = first_global_id;
   CK(cudaMemset(ctx->d_gal_maxnorm, 0, 4));
   if (N == 0) return 0;
@@ -1098,6 +1105,131 @@ extern "C" int frb_match(frb_ctx* ctx, const float* d_probes, int P, int k, floa
   CK(cudaSetDevice(ctx->device));
   return match_locked(ctx, d_probes, P, k, thr, normalize, d_scores, d_idx, d_accept, d_scores64,
                       static_cast<cudaStream_t>(stream));
+}
+
+// ---- per-identity matching over a SAMPLE gallery (evaluate_models_v2.ipynb cells 3-5)
+extern "C" int frb_gallery_upload_samples(frb_ctx* ctx, const float* samples, long long T, const long long* h_seg,
+                                          long long S, int is_device) {
+  if (!ctx) return 1;
+  if (T < 0 || S < 0 || !h_seg || h_seg[0] != 0 || h_seg[S] != T) return fail(ctx, "frb_gallery_upload_samples: bad segments");
+  std::vector<int> sid(static_cast<size_t>(T));
+  for (long long i = 0; i < S; ++i) {
+    const long long n = h_seg[i + 1] - h_seg[i];
+    if (n < 0 || n > kAggMaxRows) return fail(ctx, "frb_gallery_upload_samples: identity %lld has %lld samples (0..%d supported)", i, n, kAggMaxRows);
+    for (long long r = h_seg[i]; r < h_seg[i + 1]; ++r) sid[static_cast<size_t>(r)] = static_cast<int>(i);
+  }
+  if (int rc = frb_gallery_upload(ctx, samples, T, 0, is_device)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  if (ensure(ctx, &ctx->d_seg, &ctx->seg_cap, static_cast<size_t>(S) + 1)) return 1;
+  if (ensure(ctx, &ctx->d_sample_identity, &ctx->sid_cap, std::max<size_t>(static_cast<size_t>(T), 1))) return 1;
+  CK(cudaMemcpy(ctx->d_seg, h_seg, (static_cast<size_t>(S) + 1) * 8, cudaMemcpyHostToDevice));
+  if (T > 0) CK(cudaMemcpy(ctx->d_sample_identity, sid.data(), static_cast<size_t>(T) * 4, cudaMemcpyHostToDevice));
+  ctx->gal_S = S;
+  return 0;
+}
+
+namespace {
+// exact identity scores of probes f0..f0+fc-1 (or the listed rows) into ctx->d_id_scores [fc][S] f64
+int identity_exact_chunk(frb_ctx* ctx, const float* probes, const int* rows, int fc, int agg, int agg_k, float* d_out32,
+                         cudaStream_t st) {
+  const long long T = ctx->gal_N, S = ctx->gal_S;
+  if (ensure(ctx, &ctx->d_exact, &ctx->exact_elems, std::max<size_t>(static_cast<size_t>(fc) * T, 1))) return 1;
+  if (ensure(ctx, &ctx->d_id_scores, &ctx->id_scores_elems, std::max<size_t>(static_cast<size_t>(fc) * S, 1))) return 1;
+  if (T > 0) {
+    dim3 grid(static_cast<unsigned>(std::min<long long>((T + 7) / 8, 148 * 8)), fc);
+    match_exact_scores_kernel<<<grid, 256, 0, st>>>(ctx->d_gal, T, probes, rows, ctx->d_exact);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  dim3 g2(static_cast<unsigned>((S + 127) / 128), fc);
+  identity_reduce_kernel<<<g2, 128, 0, st>>>(ctx->d_exact, T, ctx->d_seg, S, agg, agg_k, ctx->d_id_scores, d_out32);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+}  // namespace
+
+// Full [P][S] identity score matrix (what identify_probe's identity_scores dict holds), exact f64 arithmetic, f32 out.
+extern "C" int frb_identity_scores(frb_ctx* ctx, const float* d_probes, int P, int normalize, int agg, int agg_k,
+                                   float* d_out, void* stream) {
+  if (!ctx) return 1;
+  if (P <= 0) return 0;
+  if (agg < 0 || agg > 2 || agg_k < 1) return fail(ctx, "frb_identity_scores: bad aggregation");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ctx->gal_S <= 0) return fail(ctx, "frb_identity_scores: no sample gallery uploaded");
+  float* d_norm = nullptr;
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&d_norm), static_cast<size_t>(P) * 512 * 4, st));
+  probe_prepare_kernel<<<P, 128, 0, st>>>(d_probes, normalize, d_norm, nullptr);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  for (int f0 = 0; f0 < P; f0 += kExactChunk) {
+    const int fc = std::min(kExactChunk, P - f0);
+    if (identity_exact_chunk(ctx, d_norm + static_cast<size_t>(f0) * 512, nullptr, fc, agg, agg_k,
+                             d_out + static_cast<size_t>(f0) * ctx->gal_S, st))
+      return 1;
+  }
+  CK(cudaFreeAsync(d_norm, st));
+  return 0;
+}
+
+// Top-k identities per probe.  Outputs as frb_match, with identity indices instead of gallery rows.
+extern "C" int frb_match_identities(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, int normalize, int agg,
+                                    int agg_k, float* d_scores, long long* d_idx, unsigned char* d_accept, void* stream) {
+  if (!ctx) return 1;
+  if (P <= 0) return 0;
+  if (agg < 0 || agg > 2 || agg_k < 1) return fail(ctx, "frb_match_identities: bad aggregation");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long T = ctx->gal_N, S = ctx->gal_S;
+  if (S <= 0) return fail(ctx, "frb_match_identities: no sample gallery uploaded");
+  if (k <= 0 || k > kRescore / 2) return fail(ctx, "frb_match_identities: k must be in [1, %d]", kRescore / 2);
+  constexpr int KS = kRescore / 2;  // exact top-32 samples per probe feed the candidate set
+  {
+    const size_t need = static_cast<size_t>(P) * KS;
+    if (ensure(ctx, &ctx->d_id_top_idx, &ctx->id_top_cap, need)) return 1;
+    if (ensure(ctx, &ctx->d_id_top_sc, &ctx->id_top_sc_cap, need)) return 1;
+    if (ensure(ctx, &ctx->d_id_acc, &ctx->id_acc_cap, need)) return 1;
+    if (ensure(ctx, &ctx->d_id_sc32, &ctx->id_sc32_cap, need)) return 1;
+  }
+  if (ensure(ctx, &ctx->d_scores64_tmp, &ctx->scores64_tmp_elems, static_cast<size_t>(P) * std::max(k, KS))) return 1;
+  // 1. exact top-KS SAMPLES (tensor-core filter + exact re-score + proof, or the exact scan for small galleries)
+  if (match_locked(ctx, d_probes, P, KS, -INFINITY, normalize, ctx->d_id_sc32, ctx->d_id_top_idx, ctx->d_id_acc, ctx->d_id_top_sc, st))
+    return 1;
+  // 2. candidates -> exact aggregates -> proof
+  IdentityCandParams cp;
+  cp.probes = ctx->d_probe_f32; cp.gallery = ctx->d_gal; cp.seg = ctx->d_seg; cp.sample_identity = ctx->d_sample_identity;
+  cp.top_idx = ctx->d_id_top_idx; cp.top_sc = ctx->d_id_top_sc; cp.KS = KS; cp.T = T; cp.S = S;
+  cp.agg = agg; cp.agg_k = agg_k; cp.k = k; cp.thr = thr;
+  cp.out_score = ctx->d_scores64_tmp; cp.out_idx = d_idx; cp.out_score_f32 = d_scores; cp.out_accept = d_accept;
+  cp.flagged = ctx->d_flagged;
+  identity_candidates_kernel<<<P, 128, 0, st>>>(cp);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  // 3. exact scan over all identities for the rows whose proof failed
+  ctx->h_flagged.resize(P);
+  CK(cudaMemcpyAsync(ctx->h_flagged.data(), ctx->d_flagged, static_cast<size_t>(P) * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<int> rows;
+  for (int i = 0; i < P; ++i)
+    if (ctx->h_flagged[i]) rows.push_back(i);
+  ctx->last_flagged = static_cast<int>(rows.size());
+  if (!rows.empty()) {
+    CK(cudaMemcpyAsync(ctx->d_flag_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, st));
+    const int F = static_cast<int>(rows.size());
+    for (int f0 = 0; f0 < F; f0 += kExactChunk) {
+      const int fc = std::min(kExactChunk, F - f0);
+      if (identity_exact_chunk(ctx, ctx->d_probe_f32, ctx->d_flag_rows + f0, fc, agg, agg_k, nullptr, st)) return 1;
+      match_exact_topk_kernel<<<fc, 256, 0, st>>>(ctx->d_id_scores, S, ctx->d_flag_rows + f0, k, thr, 0, ctx->d_scores64_tmp,
+                                                  d_idx, d_scores, d_accept);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+  }
+  return 0;
 }
 
 extern "C" int frb_topk_merge(frb_ctx* ctx, const double* d_in_scores64, const long long* d_in_idx, int G, int P, int k,

@@ -416,7 +416,7 @@ probe_prepare_kernel(const float* __restrict__ in, int normalize, float* __restr
   for (int j = 0; j < 4; ++j) {
     const size_t o = static_cast<size_t>(b) * 512 + t + 128 * j;
     out_f32[o] = x[j];
-    out_bf16[o] = __float2bfloat16_rn(x[j]);
+    if (out_bf16) out_bf16[o] = __float2bfloat16_rn(x[j]);
   }
 }
 
@@ -677,6 +677,141 @@ match_exact_topk_kernel(const double* __restrict__ scores, long long N, const in
         }
       break;
     }
+  }
+}
+
+// ------------------------------------------------------------------ per-identity matching over gallery SAMPLES
+// SURVEY §8f row 1 (reference evaluate_models_v2.ipynb cells 3-5: compute_all_similarities, aggregate_max / mean /
+// topk, identify_probe): the gallery holds every enrolled sample; identity i owns rows [seg[i], seg[i+1]) and its score
+// for a probe is max / mean / mean-of-top-k of the probe's similarities to those rows; identities are ranked by
+// (score desc, identity index asc) - the order Python's stable sort gives the notebook.
+enum IdAgg : int { ID_AGG_MAX = 0, ID_AGG_MEAN = 1, ID_AGG_TOPK = 2 };
+
+__device__ __forceinline__ double identity_aggregate(double* sc, int n, int agg, int agg_k) {
+  if (n <= 0) return -1.0;                       // aggregate_* return -1 for an identity without samples
+  if (agg == ID_AGG_MEAN) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += sc[i];
+    return s / n;
+  }
+  if (agg == ID_AGG_TOPK) {
+    const int kk = agg_k < n ? agg_k : n;       // np.mean(sorted(sims, reverse=True)[:min(k, len)])
+    double s = 0.0;
+    for (int r = 0; r < kk; ++r) {               // selection of the kk largest, in place
+      int b = r;
+      for (int i = r + 1; i < n; ++i)
+        if (sc[i] > sc[b]) b = i;
+      const double t = sc[r]; sc[r] = sc[b]; sc[b] = t;
+      s += sc[r];
+    }
+    return s / kk;
+  }
+  double m = sc[0];
+  for (int i = 1; i < n; ++i) m = sc[i] > m ? sc[i] : m;
+  return m;
+}
+
+// dense exact sample scores [F][T] (f64) -> identity scores [F][S] (f64 and/or f32); one thread per (probe, identity)
+__global__ void identity_reduce_kernel(const double* __restrict__ sample_scores, long long T, const long long* __restrict__ seg,
+                                       long long S, int agg, int agg_k, double* __restrict__ out64, float* __restrict__ out32) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (i >= S) return;
+  const long long r0 = seg[i];
+  const int n = static_cast<int>(seg[i + 1] - r0);
+  double buf[kAggMaxRows];
+  for (int j = 0; j < n; ++j) buf[j] = sample_scores[static_cast<size_t>(f) * T + r0 + j];
+  const double v = identity_aggregate(buf, n, agg, agg_k);
+  if (out64) out64[static_cast<size_t>(f) * S + i] = v;
+  if (out32) out32[static_cast<size_t>(f) * S + i] = static_cast<float>(v);
+}
+
+struct IdentityCandParams {
+  const float* probes;          // [P][512] normalised probes
+  const float* gallery;         // [T][512] fp32 samples
+  const long long* seg;         // [S+1]
+  const int* sample_identity;   // [T]
+  const long long* top_idx;     // [P][KS] exact top-KS sample rows (canonical order), -1 = none
+  const double* top_sc;         // [P][KS]
+  int KS;
+  long long T, S;
+  int agg, agg_k, k;
+  float thr;
+  double* out_score; long long* out_idx; float* out_score_f32; unsigned char* out_accept;
+  int* flagged;                 // 1 = the candidate set could not be proven sufficient -> exact scan
+};
+
+// One block (128 threads) per probe.  Candidates = the distinct identities among the probe's exact top-KS samples; each
+// candidate's aggregate is computed exactly (f64) from ALL its samples.  Any identity outside the candidate set has
+// every sample score <= the KS-th sample score, hence aggregate <= that bound (mean <= max): the top-k is proven when
+// the k-th candidate aggregate beats the bound strictly.
+__global__ void __launch_bounds__(128)
+identity_candidates_kernel(const IdentityCandParams p) {
+  __shared__ float s_probe[512];
+  __shared__ int s_cand[64];
+  __shared__ double s_agg[64];
+  __shared__ double s_sc[kAggMaxRows];
+  __shared__ int s_ncand;
+  const int f = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int i = t; i < 512; i += 128) s_probe[i] = p.probes[static_cast<size_t>(f) * 512 + i];
+  if (t == 0) {
+    int nc = 0;
+    for (int j = 0; j < p.KS; ++j) {
+      const long long r = p.top_idx[static_cast<size_t>(f) * p.KS + j];
+      if (r < 0) break;
+      const int id = p.sample_identity[r];
+      bool seen = false;
+      for (int c = 0; c < nc; ++c) seen |= (s_cand[c] == id);
+      if (!seen) s_cand[nc++] = id;
+    }
+    s_ncand = nc;
+  }
+  __syncthreads();
+  const int nc = s_ncand;
+  for (int c = 0; c < nc; ++c) {
+    const long long r0 = p.seg[s_cand[c]];
+    const int n = static_cast<int>(p.seg[s_cand[c] + 1] - r0);
+    for (int j = warp; j < n; j += 4) {
+      const double d = warp_dot512_f64(p.gallery + (r0 + j) * 512, s_probe, lane);
+      if (lane == 0) s_sc[j] = d;
+    }
+    __syncthreads();
+    if (t == 0) s_agg[c] = identity_aggregate(s_sc, n, p.agg, p.agg_k);
+    __syncthreads();
+  }
+  if (t == 0) {
+    const long long last = p.top_idx[static_cast<size_t>(f) * p.KS + p.KS - 1];
+    const bool saw_everything = last < 0;           // fewer than KS samples exist: all identities with samples are candidates
+    const double bound = saw_everything ? -INFINITY : p.top_sc[static_cast<size_t>(f) * p.KS + p.KS - 1];
+    double ps = INFINITY;
+    long long pi = -1;
+    bool proven = true;
+    for (int r = 0; r < p.k; ++r) {
+      double best = -INFINITY;
+      long long besti = -1;
+      for (int c = 0; c < nc; ++c) {
+        const double v = s_agg[c];
+        const long long ix = s_cand[c];
+        const bool after = (pi < 0) ? true : ((v < ps) || (v == ps && ix > pi));
+        if (after && cand_before(v, ix, best, besti)) {
+          best = v;
+          besti = ix;
+        }
+      }
+      const size_t o = static_cast<size_t>(f) * p.k + r;
+      p.out_idx[o] = besti;
+      p.out_score[o] = besti >= 0 ? best : -INFINITY;
+      p.out_score_f32[o] = besti >= 0 ? static_cast<float>(best) : -INFINITY;
+      if (besti < 0) proven = false;                        // fewer candidates than k: let the exact scan decide
+      else if (!(best > bound)) proven = proven && saw_everything;
+      if (besti >= 0) {
+        ps = best;
+        pi = besti;
+      }
+    }
+    p.out_accept[f] = (p.out_idx[static_cast<size_t>(f) * p.k] >= 0 &&
+                       p.out_score_f32[static_cast<size_t>(f) * p.k] >= p.thr) ? 1 : 0;
+    p.flagged[f] = proven ? 0 : 1;
   }
 }
 

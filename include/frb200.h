@@ -98,6 +98,22 @@ int frb_embed_profile(frb_ctx* ctx, const void* d_in, int B, int flags, float* d
  * first_global_id is added to local row numbers in every result (identity-sharded galleries). */
 int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, long long first_global_id, int is_device);
 long long frb_gallery_size(frb_ctx* ctx);
+/* ---- per-identity matching over a gallery of SAMPLES (evaluate_models_v2.ipynb cells 3-5: compute_all_similarities,
+ * aggregate_max / aggregate_mean / aggregate_topk, identify_probe) ----
+ * samples: [T][512] f32 rows (host or device); identity i owns rows [h_seg[i], h_seg[i+1]) (h_seg: S+1 int64 on the
+ * HOST, h_seg[0] = 0, h_seg[S] = T, at most 64 samples per identity).  Replaces the resident gallery. */
+int frb_gallery_upload_samples(frb_ctx* ctx, const float* samples, long long T, const long long* h_seg, long long S,
+                               int is_device);
+/* identity_scores of identify_probe for P probes: d_out [P][S] f32; agg 0 = max, 1 = mean, 2 = mean of the agg_k best;
+ * an identity without samples scores -1.  Probes are normalised like search() when normalize != 0. */
+int frb_identity_scores(frb_ctx* ctx, const float* d_probes, int P, int normalize, int agg, int agg_k, float* d_out,
+                        void* stream);
+/* top-k identities per probe ranked by (score desc, identity index asc): scores f32 [P][k], idx i64 [P][k] (identity
+ * indices, -1 = fewer than k identities), accept u8 [P] (best score >= thr).  Exact by construction: tensor-core
+ * filter over the samples, exact f64 aggregates for the candidate identities, proof, exact scan for unproven rows. */
+int frb_match_identities(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, int normalize, int agg, int agg_k,
+                         float* d_scores, long long* d_idx, unsigned char* d_accept, void* stream);
+
 /* Enrollment aggregation for S identities at once (GalleryManager._aggregate_embeddings incl. the quality filter,
  * gallery_manager.py:104-122,297-317): identity s owns rows [d_seg[s], d_seg[s+1]) of d_emb [T][512] f32 (device;
  * d_seg is S+1 int64 on the device; at most max_rows <= 64 rows each).  method: 0 mean, 1 median, 2 weighted_mean.

@@ -9,7 +9,11 @@ functions that matter are pulled out of the source files with `ast` and executed
     aug/in_<i>, aug/out_<i>   enroll_students.augment_face_for_enrollment (enroll_students.py:20-48):
                               seeded RGB crops -> the 8 augmented crops the flow embeds
     names/in, names/out       EmbeddingGenerator.extract_name_from_filename (embedding_generator.py:97-106)
+    identify/*                evaluate_models_v2.ipynb cells 3-5 (cosine_similarity, aggregate_*, identify_probe) executed
+                              on a seeded ragged sample gallery: per probe and aggregation the identity score vector,
+                              the predicted identity index (-1 = rejected) and the best score
 """
+import json
 import ast
 import os
 import types
@@ -49,6 +53,43 @@ def main():
     names = ["alice_smith_001_f3.jpg", "bob_12.png", "007_bond.jpg", "carol.jpeg", "dave_lee_x_9_9.jpg", "lfw_Aaron_Eckhart_0001.jpg"]
     pack["names/in"] = np.array(names)
     pack["names/out"] = np.array([name_fn(types.SimpleNamespace(), n) for n in names])
+    # ---- the notebook's own matcher (cells 3, 4, 5 are pure function definitions)
+    nb = json.load(open(f"{REF}/evaluate_models_v2.ipynb"))
+    from typing import Dict, List, Optional, Tuple
+    ns = dict(np=np, Dict=Dict, List=List, Optional=Optional, Tuple=Tuple)
+    for ci in (3, 4, 5):
+        exec("".join(nb["cells"][ci]["source"]), ns)
+    rng = np.random.default_rng(99)
+    counts = [1, 8, 3, 5, 8, 2, 8, 40, 4, 8, 6, 1]
+    centres = rng.standard_normal((len(counts), 512))
+    gallery, rows = {}, []
+    for i, n in enumerate(counts):
+        e = centres[i][None] + 0.9 * rng.standard_normal((n, 512))
+        e = (e / np.linalg.norm(e, axis=1, keepdims=True)).astype(np.float32)
+        gallery[f"person_{i:02d}"] = {"embeddings": e}
+        rows.append(e)
+    probes = []
+    for i in range(len(counts)):
+        p = centres[i] + 1.1 * rng.standard_normal(512)
+        probes.append(p / np.linalg.norm(p))
+    probes += [rng.standard_normal(512) for _ in range(4)]                     # impostors
+    probes[-1] = probes[-1] / np.linalg.norm(probes[-1])
+    probes = np.array(probes, dtype=np.float32)
+    probes[1] *= 1.7                                                            # not unit norm: exercises the cosine branch
+    pack["identify/samples"] = np.concatenate(rows)
+    pack["identify/counts"] = np.array(counts)
+    pack["identify/probes"] = probes
+    names = list(gallery)
+    for agg in ("max", "mean", "topk", "bogus"):
+        S, pred, best = [], [], []
+        for p in probes:
+            name, score, scores = ns["identify_probe"](p, gallery, threshold=0.3, aggregation=agg, k=3)
+            S.append([scores[n] for n in names])
+            pred.append(-1 if name is None else names.index(name))
+            best.append(score)
+        pack[f"identify/{agg}/scores"] = np.array(S, dtype=np.float64)
+        pack[f"identify/{agg}/pred"] = np.array(pred)
+        pack[f"identify/{agg}/best"] = np.array(best, dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "flows_cases.npz"), **pack)
     print({k: v.shape for k, v in pack.items()})
 
