@@ -39,6 +39,17 @@ class LayerDesc(C.Structure):
     ]
 
 
+class TrackResult(C.Structure):
+    """Mirror of `frb_track_result`."""
+
+    _fields_ = [
+        ("winner", C.c_int64), ("confidence", C.c_double), ("consensus_strength", C.c_double),
+        ("num_quality_frames", C.c_int32), ("total_frames_evaluated", C.c_int32),
+        ("candidate", C.c_int64), ("candidate_confidence", C.c_double),
+        ("candidate_num_quality_frames", C.c_int32), ("recognized", C.c_int32),
+    ]
+
+
 class WarpJob(C.Structure):
     """Mirror of `frb_warp_job`."""
 
@@ -68,6 +79,7 @@ SIGNATURES = {
     "frb_identity_scores": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "frb_match_identities": (_i, [_vp, _vp, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "frb_aggregate_templates": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "frb_track_consensus": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, C.c_double, _i, C.c_double, _vp, _vp]),
     "frb_match": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "frb_match_last_flagged": (_i, [_vp]),
     "frb_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),

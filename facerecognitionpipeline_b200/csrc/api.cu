@@ -52,6 +52,8 @@ struct frb_ctx {
   PFN_cuTensorMapEncodeIm2col_v12000 encode_im2col = nullptr;
   int driver_version = 0;
   int conv_mode = 2;  // 2 = CTA-pair kernel, 1 = 1-CTA kernel with weight multicast
+  int conv_quad = 0;  // FRB_QUAD: gemm2_sm100_kernel<., 4> for Cout >= 256 (1) / >= 128 (2) layers
+  int quad_clusters = 0;
   int use_slab = 1;   // activation-slab kernel for eligible 3x3 stride-1 layers (FRB_SLAB=0 disables)
   int use_pdl = 1;    // programmatic dependent launch between backbone kernels (FRB_PDL=0 disables)
   int match_pair = 1;   // CTA-pair match filter for P > 128 (FRB_MATCH_PAIR=0 disables)
@@ -243,10 +245,10 @@ int launch_gemm(frb_ctx* ctx, int block_n, int mode, int cluster, const CUtensor
 
 constexpr int kConvCluster = 2;
 
-template <int BN>
+template <int BN, int CL>
 int launch_gemm2_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& gp,
                    int grid, cudaStream_t st) {
-  auto kern = gemm2_sm100_kernel<BN>;
+  auto kern = gemm2_sm100_kernel<BN, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::kTotal));
@@ -258,7 +260,7 @@ int launch_gemm2_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, co
   cfg.dynamicSmemBytes = Gemm2Smem<BN>::kTotal;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
-  fill_launch_attrs(attr, 2);
+  fill_launch_attrs(attr, CL);
   cfg.attrs = attr;
   cfg.numAttrs = ctx->use_pdl ? 2 : 1;
   CK(cudaLaunchKernelEx(&cfg, kern, a, a2, b, gp));
@@ -266,14 +268,43 @@ int launch_gemm2_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, co
   return 0;
 }
 
+// How many 4-CTA clusters of the quad kernel can be resident at once (the GPCs of a B200 hold 16-20 SMs, so 4-CTA
+// clusters strand a few SMs: 33 clusters = 132 of 148).  The persistent tile loop needs exactly one wave.
+int quad_max_clusters(frb_ctx* ctx) {
+  if (ctx->quad_clusters > 0) return ctx->quad_clusters;
+  auto kern = gemm2_sm100_kernel<256, 4>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<256>::kTotal);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctx->num_sms / 4 * 4);
+  cfg.blockDim = dim3(kGemm2Threads);
+  cfg.dynamicSmemBytes = Gemm2Smem<256>::kTotal;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = ctx->num_sms / 4 * 7 / 8;
+  }
+  ctx->quad_clusters = n;
+  return n;
+}
+
 // Convolution launch: CTA-pair kernel (cta_group::2) by default; FRB_CONV_MODE=1 selects the
 // 1-CTA kernel with 2-way weight multicast (kept for A/B profiling and as the FC/GEMM core).
 int launch_conv(frb_ctx* ctx, int block_n, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
                 const GemmParams& gp, int grid, cudaStream_t st) {
   if (ctx->conv_mode == 1) return launch_gemm(ctx, block_n, A_IM2COL, kConvCluster, a, a2, b, gp, grid, st);
-  if (block_n == 64) return launch_gemm2_t<64>(ctx, a, a2, b, gp, grid, st);
-  if (block_n == 128) return launch_gemm2_t<128>(ctx, a, a2, b, gp, grid, st);
-  if (block_n == 256) return launch_gemm2_t<256>(ctx, a, a2, b, gp, grid, st);
+  if (gp.quad) {
+    if (block_n == 128) return launch_gemm2_t<128, 4>(ctx, a, a2, b, gp, grid, st);
+    if (block_n == 256) return launch_gemm2_t<256, 4>(ctx, a, a2, b, gp, grid, st);
+    return fail(ctx, "unsupported quad conv block_n=%d", block_n);
+  }
+  if (block_n == 64) return launch_gemm2_t<64, 2>(ctx, a, a2, b, gp, grid, st);
+  if (block_n == 128) return launch_gemm2_t<128, 2>(ctx, a, a2, b, gp, grid, st);
+  if (block_n == 256) return launch_gemm2_t<256, 2>(ctx, a, a2, b, gp, grid, st);
   return fail(ctx, "unsupported conv block_n=%d", block_n);
 }
 
@@ -424,8 +455,18 @@ int setup_conv(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, c
   }
   const int ktot = (gp->num_kb_main + gp->num_kb_sc) * 64;
   *block_n = pick_block_n(L.cout);
-  if (make_tmap_2d(ctx, tmB, d_w, ktot, L.cout, *block_n / kConvCluster)) return 1;
   const int m_super = ((gp->M + 127) / 128 + kConvCluster - 1) / kConvCluster;
+  // quad clusters (weight multicast across two CTA pairs) where the layer is bound by L2->SM ingest: Cout >= 256
+  // (FRB_QUAD: 0 = never, 1 = block_n 256, 2 = block_n >= 128); not with the per-image dataflow schedule
+  gp->quad = (ctx->conv_mode == 2 && !ctx->use_dataflow && ctx->conv_quad > 0 &&
+              (*block_n == 256 || (*block_n == 128 && ctx->conv_quad >= 2)) && m_super >= 2) ? 1 : 0;
+  if (gp->quad) {
+    if (make_tmap_2d(ctx, tmB, d_w, ktot, L.cout, *block_n / 4)) return 1;
+    const int units = (m_super + 1) / 2 * (L.cout / *block_n);
+    *grid = std::min(units, quad_max_clusters(ctx)) * 4;
+    return 0;
+  }
+  if (make_tmap_2d(ctx, tmB, d_w, ktot, L.cout, *block_n / kConvCluster)) return 1;
   const int units = m_super * (L.cout / *block_n);
   *grid = std::min(units, ctx->num_sms / kConvCluster) * kConvCluster;
   return 0;
@@ -463,6 +504,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   cudaDriverGetVersion(&ctx->driver_version);
   if (const char* e = getenv("FRB_CONV_MODE")) ctx->conv_mode = atoi(e);
   if (const char* e = getenv("FRB_SLAB")) ctx->use_slab = atoi(e);
+  if (const char* e = getenv("FRB_QUAD")) ctx->conv_quad = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
   if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
   if (const char* e = getenv("FRB_MATCH_PAIR")) ctx->match_pair = atoi(e);
@@ -911,6 +953,24 @@ extern "C" int frb_aggregate_templates(frb_ctx* ctx, const float* d_emb, const l
   std::lock_guard<std::mutex> lk(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   aggregate_templates_kernel<<<S, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_emb, d_seg, method, min_similarity, d_templates, d_kept);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+// Track-level consensus: FaceMatcher._aggregate_matches / _get_best_candidate for T tracks at once.
+extern "C" int frb_track_consensus(frb_ctx* ctx, const long long* d_top_idx, const float* d_top_score, int k_stride,
+                                   const long long* d_seg, int T, int max_frames, double min_quality, int min_frames,
+                                   double threshold, frb_track_result* d_out, void* stream) {
+  if (!ctx) return 1;
+  if (T <= 0) return 0;
+  static_assert(sizeof(frb_track_result) == sizeof(frb_track_result_dev), "frb_track_result layout");
+  if (k_stride < 1) return fail(ctx, "frb_track_consensus: k_stride must be >= 1");
+  if (max_frames > kTrackMaxFrames) return fail(ctx, "frb_track_consensus: at most %d frames per track (got %d)", kTrackMaxFrames, max_frames);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  track_consensus_kernel<<<T, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_top_idx, d_top_score, k_stride, d_seg, min_quality, min_frames, threshold, reinterpret_cast<frb_track_result_dev*>(d_out));
   CK(cudaGetLastError());
   ctx->launches++;
   return 0;

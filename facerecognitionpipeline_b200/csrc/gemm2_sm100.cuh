@@ -35,6 +35,18 @@ __device__ __forceinline__ void tma2_load_2d(const CUtensorMap* m, uint32_t bar_
       "l"(kTmaMemDescDefault)
       : "memory");
 }
+// multicast form: the box lands at the same offset in every CTA of `mask`; each destination's bytes complete on the
+// barrier at the same offset in the EVEN CTA of that destination's pair (peer bit of `bar_addr` cleared - CUTLASS
+// SM100_TMA_2SM_LOAD_MULTICAST passes its own barrier address & Sm100MmaPeerBitMask)
+__device__ __forceinline__ void tma2_load_2d_mcast(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "h"(mask), "r"(c0), "r"(c1),
+      "l"(kTmaMemDescDefault)
+      : "memory");
+}
 __device__ __forceinline__ void tma2_load_im2col_4d(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c,
                                                     int w, int h, int n, uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -119,6 +131,13 @@ __device__ __forceinline__ void umma2_commit_pair(uint64_t* bar) {  // arrive on
       : "memory");
 }
 
+__device__ __forceinline__ void umma2_commit_mask(uint64_t* bar, uint16_t mask) {  // arrive on `bar` in every CTA of mask
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+
 constexpr int kGemm2Threads = 320;  // producer warp + MMA warp + 8 epilogue warps
 
 template <int BLOCK_N>
@@ -133,7 +152,11 @@ struct Gemm2Smem {
   static constexpr int kTotal = kStages * kStageBytes + 512 + kEpiBytes + 1024;
 };
 
-template <int BLOCK_N>
+// CL = 2: one CTA pair per cluster.  CL = 4 ("quad"): two pairs that work on neighbouring 256-row tiles of the SAME
+// weight tile in lock step; each CTA fetches a QUARTER of the weight tile and multicasts it to the CTA of the same
+// pair rank in the other pair, which halves the weight L2->SM traffic again (the 14x14 layers are bound by the
+// ~6300 B/clk the L2 slices deliver chip-wide: 231 MB of im2col operand + 231 MB of weights per layer at batch 256).
+template <int BLOCK_N, int CL = 2>
 __global__ void __launch_bounds__(kGemm2Threads, 1)
 gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -154,15 +177,21 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // shuffle-broadcast makes the warp index provably warp-uniform for ptxas (uniform branches / registers)
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int crank = static_cast<int>(cluster_ctarank());
+  static_assert(CL == 2 || CL == 4, "cluster of one or two CTA pairs");
+  constexpr int PAIRS = CL / 2;
+  const int crank_full = static_cast<int>(cluster_ctarank());
+  const int crank = crank_full & 1;        // rank inside the CTA pair
+  const int pair_id = crank_full >> 1;     // which pair of the cluster
+  const int lead_rank = crank_full & ~1;   // cluster rank of this pair's leader
   const bool leader = (crank == 0);
 
   const int m_pairs = ((p.M + kBlockM - 1) / kBlockM + 1) / 2;  // 256-row super tiles
+  const int m_units = (m_pairs + PAIRS - 1) / PAIRS;            // a cluster takes PAIRS neighbouring super tiles
   const int n_tiles = p.N / BLOCK_N;
   const int num_kb = p.num_kb_main + p.num_kb_sc;
-  const int total_tiles = m_pairs * n_tiles;
-  const int first_tile = blockIdx.x >> 1;
-  const int tile_step = gridDim.x >> 1;
+  const int total_tiles = m_units * n_tiles;
+  const int first_tile = blockIdx.x / CL;
+  const int tile_step = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -170,7 +199,7 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (p.num_kb_sc > 0) prefetch_tmap(&tmA2);
     for (int i = 0; i < S::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], PAIRS);  // every pair's MMAs must have retired: peers multicast into this stage
     }
     for (int i = 0; i < S::kAccStages; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -207,11 +236,13 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), 0);
+    const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), lead_rank);
+    const uint32_t full_peerbit0 = smem_u32(&full_bar[0]) & 0xFEFFFFFFu;   // multicast form: "even CTA of each destination"
+    const uint16_t b_mask = static_cast<uint16_t>((1u << crank) | (1u << (crank + 2)));
     const int pq = p.P * p.Q;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int n_tile = tile % n_tiles;
-      const int m_tile = (tile / n_tiles) * 2 + crank;
+      const int m_tile = ((tile / n_tiles) * PAIRS + pair_id) * 2 + crank;
       const int m0 = (m_tile * kBlockM < p.M) ? m_tile * kBlockM : 0;  // padding tile: re-read tile 0, stores masked
       const int img = m0 / pq;
       const int rem = m0 - img * pq;
@@ -219,7 +250,7 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int qq = rem - pp * p.Q;
       const int w_main = qq * p.stride - p.pad, h_main = pp * p.stride - p.pad;
       const int w_sc = qq * p.sc_stride, h_sc = pp * p.sc_stride;
-      const int b_row = n_tile * BLOCK_N + crank * (BLOCK_N / 2);
+      const int b_row = n_tile * BLOCK_N + crank * (BLOCK_N / 2) + pair_id * (BLOCK_N / CL);
       if (p.progress != nullptr && p.wait_target >= 0) {
         const int m_last = min(m0 + kBlockM, p.M) - 1;
         wait_images(p.progress, img, m_last / pq, p.wait_target);
@@ -238,7 +269,11 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                   static_cast<uint16_t>(tap_r));
             else
               tma2_load_im2col_4d(&tmA2, full_leader, sa, cc * kBlockK, w_sc, h_sc, img, 0, 0);
-            tma2_load_2d(&tmB, full_leader, sb, kb * kBlockK, b_row);
+            if (CL == 2)
+              tma2_load_2d(&tmB, full_leader, sb, kb * kBlockK, b_row);
+            else
+              tma2_load_2d_mcast(&tmB, full_peerbit0 + 8 * stage, static_cast<uint8_t*>(sb) + pair_id * (S::kBBytes / 2),
+                                 kb * kBlockK, b_row, b_mask);
           }
         }
         __syncwarp();
@@ -287,8 +322,8 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k)
                 umma2_bf16_ss_lo(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma2_commit_pair(&empty_bar[stage]);   // frees this stage in both CTAs
-              if (kb == num_kb - 1) umma2_commit_pair(&tmem_full_bar[acc]);   // accumulators ready in both CTAs
+              umma2_commit_mask(&empty_bar[stage], static_cast<uint16_t>((1u << CL) - 1));   // one arrival in every CTA of the cluster
+              if (kb == num_kb - 1) umma2_commit_mask(&tmem_full_bar[acc], static_cast<uint16_t>(3u << lead_rank));   // accumulators ready in both CTAs of the pair
             }
           }
           __syncwarp();
@@ -313,7 +348,7 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int n_tile = tile % n_tiles;
-      const int m_tile = (tile / n_tiles) * 2 + crank;
+      const int m_tile = ((tile / n_tiles) * PAIRS + pair_id) * 2 + crank;
       const int row = quad * 32 + lane;
       const int m = m_tile * kBlockM + row;
       const bool valid = m < p.M;
@@ -406,7 +441,7 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), lead_rank));
       if (p.progress != nullptr) signal_rows(p.progress, valid, img, BLOCK_N / 64, p.sig_fence != 0);  // this warp stored BLOCK_N/64 chunks per row
       if (++acc == S::kAccStages) {
         acc = 0;

@@ -46,6 +46,7 @@ struct GemmParams {
   int* progress;
   int wait_target;
   int sig_fence;  // experiments only: 0 drops the release fence before the progress update (UNSAFE)
+  int quad;       // host side only: launch gemm2_sm100_kernel<., 4> (two CTA pairs sharing the weight tile by multicast)
 };
 
 template <int BLOCK_N>

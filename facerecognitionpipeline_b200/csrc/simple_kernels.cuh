@@ -815,6 +815,128 @@ identity_candidates_kernel(const IdentityCandParams p) {
   }
 }
 
+// ------------------------------------------------------------------ track-level consensus
+// FaceMatcher._aggregate_matches + _get_best_candidate (face_matcher.py:321-385) for T tracks at once.  Track t owns
+// frames [seg[t], seg[t+1]); a frame is its top-1 (gallery row, f32 score) from frb_match, row < 0 = the frame had no
+// match and is skipped (face_matcher.py:180-181).  Votes are counted the way collections.Counter.most_common orders
+// them (count descending, first occurrence first); means follow numpy's pairwise float64 summation bit for bit.
+struct frb_track_result_dev {      // == frb_track_result (include/frb200.h)
+  long long winner;                // consensus identity (gallery row) or -1
+  double confidence;               // mean of the winner's quality-frame scores
+  double consensus_strength;       // winner votes / quality frames
+  int num_quality_frames;          // winner's quality frames
+  int total_frames_evaluated;      // frames that had a match
+  long long candidate;             // _get_best_candidate identity (-1 when the track has no matched frame)
+  double candidate_confidence;
+  int candidate_num_quality_frames;
+  int recognized;                  // 1 = consensus reached and confidence >= threshold
+};
+
+// numpy pairwise_sum of float64 (numpy/_core/src/umath/loops_utils.h.src): < 8 sequential, <= 128 eight
+// interleaved accumulators, above that recursive halves (multiples of 8)
+__device__ inline double np_pairwise_sum(const double* a, int n) {
+  if (n < 8) {
+    double res = 0.;
+    for (int i = 0; i < n; ++i) res += a[i];
+    return res;
+  }
+  if (n <= 128) {
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+constexpr int kTrackMaxFrames = 1024;
+
+// one block per track; the vote itself is a short sequential scan (tracks hold tens of frames), done by thread 0
+// on shared-memory copies the whole block loads
+__global__ void __launch_bounds__(128)
+track_consensus_kernel(const long long* __restrict__ top_idx, const float* __restrict__ top_score, int stride,
+                       const long long* __restrict__ seg, double min_quality, int min_frames, double thr,
+                       frb_track_result_dev* __restrict__ out) {
+  __shared__ long long s_id[kTrackMaxFrames];
+  __shared__ double s_sc[kTrackMaxFrames];
+  __shared__ double s_tmp[kTrackMaxFrames];
+  const int t = blockIdx.x;
+  const long long f0 = seg[t];
+  int F = static_cast<int>(seg[t + 1] - f0);
+  if (F > kTrackMaxFrames) F = kTrackMaxFrames;   // the entry point rejects longer tracks; never overrun shared memory
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    s_id[i] = top_idx[(f0 + i) * stride];
+    s_sc[i] = static_cast<double>(top_score[(f0 + i) * stride]);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  frb_track_result_dev r;
+  r.winner = -1; r.confidence = 0.; r.consensus_strength = 0.; r.num_quality_frames = 0; r.total_frames_evaluated = 0;
+  r.candidate = -1; r.candidate_confidence = 0.; r.candidate_num_quality_frames = 0; r.recognized = 0;
+  int total = 0, voters = 0;
+  for (int i = 0; i < F; ++i) {
+    if (s_id[i] < 0) continue;
+    ++total;
+    if (s_sc[i] >= min_quality) ++voters;
+  }
+  r.total_frames_evaluated = total;
+  // Counter.most_common over a pool (quality frames, or every matched frame): best and runner-up by
+  // (count desc, first occurrence asc)
+  auto rank2 = [&](bool quality_only, long long* id1, int* c1, int* c2) {
+    *id1 = -1; *c1 = 0; *c2 = 0;
+    long long id2 = -1;
+    for (int i = 0; i < F; ++i) {
+      const long long id = s_id[i];
+      if (id < 0 || (quality_only && !(s_sc[i] >= min_quality))) continue;
+      bool first = true;
+      for (int j = 0; j < i && first; ++j)
+        if (s_id[j] == id && !(quality_only && !(s_sc[j] >= min_quality))) first = false;
+      if (!first) continue;
+      int c = 0;
+      for (int j = i; j < F; ++j)
+        if (s_id[j] == id && !(quality_only && !(s_sc[j] >= min_quality))) ++c;
+      if (c > *c1) { id2 = *id1; *c2 = *c1; *id1 = id; *c1 = c; }
+      else if (c > *c2) { id2 = id; *c2 = c; }
+    }
+    (void)id2;
+  };
+  auto mean_of = [&](long long id, bool quality_only, int* n_out) {
+    int n = 0;
+    for (int i = 0; i < F; ++i)
+      if (s_id[i] == id && !(quality_only && !(s_sc[i] >= min_quality))) s_tmp[n++] = s_sc[i];
+    *n_out = n;
+    return np_pairwise_sum(s_tmp, n) / static_cast<double>(n);
+  };
+  if (total > 0) {
+    const bool pool_quality = voters > 0;            // _get_best_candidate: quality frames, else all frames
+    long long cid; int cc1, cc2;
+    rank2(pool_quality, &cid, &cc1, &cc2);
+    r.candidate = cid;
+    r.candidate_confidence = mean_of(cid, pool_quality, &r.candidate_num_quality_frames);
+  }
+  if (voters >= min_frames) {
+    long long wid; int c1, c2;
+    rank2(true, &wid, &c1, &c2);
+    const double share = static_cast<double>(c1) / static_cast<double>(voters);
+    bool agreed = share > 0.5;
+    if (!agreed && c2 > 0) agreed = share > 0.4 && c1 >= 2 * c2;
+    if (agreed) {
+      int n;
+      const double m = mean_of(wid, true, &n);
+      if (!(m < thr)) {
+        r.winner = wid; r.confidence = m; r.consensus_strength = share; r.num_quality_frames = n; r.recognized = 1;
+      }
+    }
+  }
+  out[t] = r;
+}
+
 // merge G per-rank top-k lists (after an all-gather) into the global top-k; one thread per probe.
 // in_score/in_idx: [G][P][k]
 __global__ void topk_merge_kernel(const double* __restrict__ in_score, const long long* __restrict__ in_idx, int G,

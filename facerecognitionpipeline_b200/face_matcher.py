@@ -4,7 +4,8 @@
 Here both halves run on the B200 in one C-ABI call (`frb_embed_match_host`), and
 `match_faces_batch` (new) does it for a whole list of crops at once.  The multi-frame consensus
 (`_aggregate_matches`, face_matcher.py:321-363) and result dictionaries are host glue with the
-reference's exact decision rules and field names.
+reference's exact decision rules and field names; `consensus_on_device` / `match_tracks_batch` run the
+same decision for many tracks in one launch (`frb_track_consensus`).
 """
 from __future__ import annotations
 
@@ -66,6 +67,40 @@ def best_candidate(frame_matches: List[Dict]) -> Dict:
         "confidence": float(np.mean(scores)),
         "num_quality_frames": len(scores),
     }
+
+
+def consensus_on_device(top_idx, top_score, frames_per_track, similarity_threshold: float, device: int = 0):
+    """`consensus` + `best_candidate` for many tracks in one launch (`frb_track_consensus`).
+
+    top_idx / top_score: [F] or [F][k] (column 0 = top-1) gallery rows (int64, < 0 = frame without a match) and f32
+    scores of every frame of every track, numpy or CUDA torch tensors (e.g. straight from frb_match);
+    frames_per_track: the T track lengths.  Returns a numpy record array with the fields of `frb_track_result`."""
+    import torch
+
+    from . import _native
+    ctx = _native.default_context(device)
+    dev = torch.device("cuda", device)
+    ix = torch.as_tensor(top_idx).to(device=dev, dtype=torch.int64).contiguous()
+    sc = torch.as_tensor(top_score).to(device=dev, dtype=torch.float32).contiguous()
+    stride = 1 if ix.dim() == 1 else int(ix.shape[1])
+    if ix.shape != sc.shape:
+        raise ValueError("top_idx and top_score differ in shape")
+    counts = np.asarray(frames_per_track, dtype=np.int64).reshape(-1)
+    T = len(counts)
+    if int(counts.sum()) != int(ix.shape[0]):
+        raise ValueError(f"frames_per_track sums to {int(counts.sum())} but {int(ix.shape[0])} frames were given")
+    dt = np.dtype([("winner", "<i8"), ("confidence", "<f8"), ("consensus_strength", "<f8"), ("num_quality_frames", "<i4"),
+                   ("total_frames_evaluated", "<i4"), ("candidate", "<i8"), ("candidate_confidence", "<f8"),
+                   ("candidate_num_quality_frames", "<i4"), ("recognized", "<i4")])
+    assert dt.itemsize == 56
+    if T == 0:
+        return np.zeros(0, dt)
+    seg = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)])).to(dev)
+    out = torch.empty((T, dt.itemsize), dtype=torch.uint8, device=dev)
+    ctx.frb_track_consensus(ix.data_ptr(), sc.data_ptr(), stride, seg.data_ptr(), T, int(counts.max()), MIN_QUALITY_SCORE,
+                            MIN_QUALITY_FRAMES, float(similarity_threshold), out.data_ptr(),
+                            torch.cuda.current_stream(dev).cuda_stream)
+    return out.cpu().numpy().view(dt).reshape(T)
 
 
 class FaceMatcher:
@@ -149,6 +184,61 @@ class FaceMatcher:
         return {"track_id": track_id, "recognized": True, "student_id": final["student_id"], "name": final["name"],
                 "confidence": final["confidence"], "method": self.aggregation_method, "num_frames": len(frame_matches),
                 "frame_matches": frame_matches, "metadata": metadata, "timestamp": datetime.now().isoformat()}
+
+    def match_tracks_batch(self, tracks: List[List[np.ndarray]], top_k: int = 3) -> List[Optional[Dict]]:
+        """The decision part of `match_track` for many tracks at once: every crop of every track goes through ONE
+        embed stream, one device match and one consensus launch; results come back in a single copy.  Entry t is
+        None for a track without any matched frame, else the `match_track` dictionary fields that do not depend on
+        files (recognized / student_id / name / confidence / ... / best_candidate / frame top-1 list)."""
+        import torch
+        counts = [len(t) for t in tracks]
+        crops = [c for t in tracks for c in t]
+        if not crops:
+            return [None] * len(tracks)
+        if len(self.gallery.students) == 0:
+            return [None] * len(tracks)
+        emb = self.embedder.extract_embeddings_batch(crops, normalize=True)
+        self.gallery._ensure_resident()
+        ctx, dev = self.gallery._context(), torch.device("cuda", self.gallery._device)
+        F, k = len(crops), int(top_k)
+        d_q = torch.from_numpy(np.ascontiguousarray(emb, dtype=np.float32)).to(dev)
+        d_sc = torch.empty((F, k), dtype=torch.float32, device=dev)
+        d_ix = torch.empty((F, k), dtype=torch.int64, device=dev)
+        d_ac = torch.empty((F,), dtype=torch.uint8, device=dev)
+        ctx.frb_match(d_q.data_ptr(), F, k, float(self.similarity_threshold), 1, d_sc.data_ptr(), d_ix.data_ptr(),
+                      d_ac.data_ptr(), None, torch.cuda.current_stream(dev).cuda_stream)
+        res = consensus_on_device(d_ix, d_sc, counts, self.similarity_threshold, self.gallery._device)
+        ix, sc = d_ix.cpu().numpy(), d_sc.cpu().numpy()
+        ids = self.gallery._ids
+
+        def ident(row):
+            sid = ids[int(row)]
+            return sid, self.gallery.students[sid].name
+
+        out, f0 = [], 0
+        for t, n in enumerate(counts):
+            r = res[t]
+            if r["total_frames_evaluated"] == 0:
+                out.append(None)
+                f0 += n
+                continue
+            frames = [{"student_id": ident(ix[f, 0])[0], "name": ident(ix[f, 0])[1], "score": float(sc[f, 0])}
+                      for f in range(f0, f0 + n) if ix[f, 0] >= 0]
+            f0 += n
+            if r["recognized"]:
+                sid, name = ident(r["winner"])
+                out.append({"recognized": True, "student_id": sid, "name": name, "confidence": float(r["confidence"]),
+                            "consensus_strength": float(r["consensus_strength"]),
+                            "num_quality_frames": int(r["num_quality_frames"]), "method": self.aggregation_method,
+                            "num_frames": int(r["total_frames_evaluated"]), "frame_matches": frames})
+            else:
+                sid, name = ident(r["candidate"])
+                out.append({"recognized": False, "reason": "below_threshold",
+                            "best_candidate": {"student_id": sid, "name": name,
+                                               "confidence": float(r["candidate_confidence"]),
+                                               "num_quality_frames": int(r["candidate_num_quality_frames"])},
+                            "frame_matches": frames})
+        return out
 
     def _aggregate_matches(self, frame_matches: List[Dict], all_scores: Dict[str, List[float]]) -> Optional[Dict]:
         return consensus(frame_matches, self.similarity_threshold)

@@ -121,6 +121,27 @@ int frb_match_identities(frb_ctx* ctx, const float* d_probes, int P, int k, floa
  * survived the quality filter (may be NULL). */
 int frb_aggregate_templates(frb_ctx* ctx, const float* d_emb, const long long* d_seg, int S, int max_rows, int method,
                             float min_similarity, float* d_templates, int* d_kept, void* stream);
+/* ---- track-level consensus (FaceMatcher._aggregate_matches, face_matcher.py:321-363, and _get_best_candidate,
+ * :365-385) for T tracks at once.  Frame f of the stream is described by its top-1 match as frb_match wrote it:
+ * d_top_idx[f * k_stride] (gallery row, < 0 = the frame had no match and is skipped like face_matcher.py:180-181) and
+ * d_top_score[f * k_stride]; track t owns frames [d_seg[t], d_seg[t+1]) (T+1 int64 on the device, at most max_frames
+ * <= 1024 each).  Frames scoring >= min_quality (0.55) vote; >= min_frames (3) voters; the winner needs > 50 % of the
+ * votes or > 40 % and twice the runner-up (ties: first occurrence, as Counter.most_common); its mean score (numpy's
+ * float64 pairwise sum) must reach `threshold`. */
+typedef struct frb_track_result {
+  long long winner;               /* consensus gallery row, -1 = not recognised */
+  double confidence;              /* 'confidence' */
+  double consensus_strength;      /* 'consensus_strength' */
+  int num_quality_frames;         /* 'num_quality_frames' */
+  int total_frames_evaluated;     /* 'total_frames_evaluated' */
+  long long candidate;            /* _get_best_candidate: 'student_id' row (-1: no matched frame) */
+  double candidate_confidence;
+  int candidate_num_quality_frames;
+  int recognized;
+} frb_track_result;
+int frb_track_consensus(frb_ctx* ctx, const long long* d_top_idx, const float* d_top_score, int k_stride,
+                        const long long* d_seg, int T, int max_frames, double min_quality, int min_frames,
+                        double threshold, frb_track_result* d_out, void* stream);
 /* d_probes: [P][512] f32.  normalize != 0 applies q/(||q||+1e-8) first (search()).
  * Outputs (device): scores f32 [P][k], idx i64 [P][k] (global ids, -1 = fewer than k rows),
  * accept u8 [P] (top-1 score >= thr), scores64 f64 [P][k] (optional, for cross-rank merge). */

@@ -9,6 +9,8 @@ functions that matter are pulled out of the source files with `ast` and executed
     aug/in_<i>, aug/out_<i>   enroll_students.augment_face_for_enrollment (enroll_students.py:20-48):
                               seeded RGB crops -> the 8 augmented crops the flow embeds
     names/in, names/out       EmbeddingGenerator.extract_name_from_filename (embedding_generator.py:97-106)
+    tracks/*                  FaceMatcher._aggregate_matches / _get_best_candidate (face_matcher.py:321-385) executed on
+                              seeded synthetic tracks: per-frame top-1 (identity, f32 score) -> the decision fields
     identify/*                evaluate_models_v2.ipynb cells 3-5 (cosine_similarity, aggregate_*, identify_probe) executed
                               on a seeded ragged sample gallery: per probe and aggregation the identity score vector,
                               the predicted identity index (-1 = rejected) and the best score
@@ -34,7 +36,9 @@ def extract(path, name, cls=None):
     mod = ast.Module(body=[fn], type_ignores=[])
     from pathlib import Path
     from typing import Dict, List, Tuple
-    ns = dict(cv2=cv2, np=np, List=List, Dict=Dict, Tuple=Tuple, Path=Path)
+    from collections import Counter
+    from typing import Optional
+    ns = dict(cv2=cv2, np=np, List=List, Dict=Dict, Tuple=Tuple, Path=Path, Counter=Counter, Optional=Optional)
     exec(compile(mod, path, "exec"), ns)
     return ns[name]
 
@@ -90,6 +94,34 @@ def main():
         pack[f"identify/{agg}/scores"] = np.array(S, dtype=np.float64)
         pack[f"identify/{agg}/pred"] = np.array(pred)
         pack[f"identify/{agg}/best"] = np.array(best, dtype=np.float64)
+    # ---- track-level consensus: the reference's own methods on synthetic tracks
+    agg_fn = extract(f"{REF}/face_matcher.py", "_aggregate_matches", cls="FaceMatcher")
+    cand_fn = extract(f"{REF}/face_matcher.py", "_get_best_candidate", cls="FaceMatcher")
+    rng = np.random.default_rng(2024)
+    seg, ids, scores, thr_list, rows = [0], [], [], [], []
+    for t in range(400):
+        F = int(rng.choice([0, 1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 30, 64, 129, 150, 300]))
+        pool = rng.choice(50, size=int(rng.integers(1, 5)), replace=False)
+        fid = rng.choice(pool, size=F, p=None)
+        lo = float(rng.choice([0.3, 0.5, 0.56]))
+        sc = rng.uniform(lo, 0.95, size=F).astype(np.float32)
+        if F and rng.random() < 0.3:
+            fid[rng.integers(0, F, max(1, F // 5))] = -1            # frames without any match (skipped)
+        thr = float(rng.choice([0.4, 0.5, 0.6, 0.7]))
+        fm = [dict(student_id=f"STU{i:04d}", name=f"n{i}", score=float(s)) for i, s in zip(fid, sc) if i >= 0]
+        self_ = types.SimpleNamespace(similarity_threshold=thr)
+        a = agg_fn(self_, fm, {}) if fm else None
+        c = cand_fn(self_, fm, {}) if fm else None
+        rows.append([
+            1 if a else 0, int(a["student_id"][3:]) if a else -1, a["confidence"] if a else 0.0,
+            a["consensus_strength"] if a else 0.0, a["num_quality_frames"] if a else 0, len(fm),
+            int(c["student_id"][3:]) if c else -1, c["confidence"] if c else 0.0, c["num_quality_frames"] if c else 0])
+        ids += list(fid); scores += list(sc); seg.append(seg[-1] + F); thr_list.append(thr)
+    pack["tracks/seg"] = np.array(seg, np.int64)
+    pack["tracks/ids"] = np.array(ids, np.int64)
+    pack["tracks/scores"] = np.array(scores, np.float32)
+    pack["tracks/thr"] = np.array(thr_list, np.float64)
+    pack["tracks/out"] = np.array(rows, np.float64)    # recognized, winner, confidence, strength, nq, total, cand, cand_conf, cand_nq
     np.savez_compressed(os.path.join(OUT, "flows_cases.npz"), **pack)
     print({k: v.shape for k, v in pack.items()})
 
