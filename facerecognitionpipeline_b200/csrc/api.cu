@@ -34,6 +34,7 @@ struct Plan {  // per-batch-size launch plan of the backbone
   std::vector<CUtensorMap> tmA, tmA2, tmB;
   std::vector<GemmParams> gp;
   std::vector<int> block_n, grid;
+  size_t tail_flags = 0;           // split-K flags of all layers (zeroed at the start of every embed)
   std::vector<int> use_slab;       // 1 = conv_slab_sm100_kernel (3x3 stride-1, W in {28,56,112})
   std::vector<SlabParams> sp;
   std::vector<int> slab_smem;
@@ -52,6 +53,9 @@ struct frb_ctx {
   PFN_cuTensorMapEncodeIm2col_v12000 encode_im2col = nullptr;
   int driver_version = 0;
   int conv_mode = 2;  // 2 = CTA-pair kernel, 1 = 1-CTA kernel with weight multicast
+  int tail_split = 0;  // FRB_TAIL_SPLIT=1: split-K for the last partial round of the pair conv kernel (see TileItem)
+  float* d_tail_partial = nullptr; size_t tail_partial_cap = 0;
+  int* d_tail_flags = nullptr; size_t tail_flags_cap = 0;
   int conv_quad = 0;  // FRB_QUAD: gemm2_sm100_kernel<., 4> for Cout >= 256 (1) / >= 128 (2) layers
   int quad_clusters = 0;
   int use_slab = 1;   // activation-slab kernel for eligible 3x3 stride-1 layers (FRB_SLAB=0 disables)
@@ -469,7 +473,36 @@ int setup_conv(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, c
   if (make_tmap_2d(ctx, tmB, d_w, ktot, L.cout, *block_n / kConvCluster)) return 1;
   const int units = m_super * (L.cout / *block_n);
   *grid = std::min(units, ctx->num_sms / kConvCluster) * kConvCluster;
+  // split-K for the last, partially filled round (14x14 layers at batch 256: 196 tiles on 74 pairs = 2 rounds + 48
+  // tiles; cut in 3 K ranges those 48 tiles are 144 items = 2 short sub-rounds, 2.67 rounds instead of 3)
+  gp->tail_split = 0;
+  const int pairs = *grid / 2;
+  if (ctx->tail_split && ctx->conv_mode == 2 && !ctx->use_dataflow && gp->num_kb_sc == 0 && units >= pairs && units % pairs) {
+    const int full = units / pairs, rem = units % pairs;
+    int best = 1;
+    double best_cost = 1.0;
+    for (int sp = 2; sp <= 4; ++sp) {
+      if (gp->num_kb_main % sp) continue;
+      const double cost = static_cast<double>((rem * sp + pairs - 1) / pairs) / sp + 0.05;  // + the partial round trip
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+    }
+    if (best > 1 && (1.0 - best_cost) / (full + 1) >= 0.02) gp->tail_split = best;
+    if (const char* e = getenv("FRB_TS_DEBUG")) gp->tail_debug = atoi(e);
+    if (const char* e = getenv("FRB_TS_FORCE")) gp->tail_split = atoi(e);
+  }
   return 0;
+}
+
+// split-K scratch of one conv launch: rem tiles x (split-1) fp32 partial tiles + rem flags
+void tail_split_needs(const GemmParams& gp, int block_n, int grid, size_t* partial_floats, size_t* flags) {
+  *partial_floats = 0;
+  *flags = 0;
+  if (gp.tail_split <= 1) return;
+  const int pairs = grid / 2;
+  const int units = (((gp.M + 127) / 128 + 1) / 2) * (gp.N / block_n);
+  const int rem = units % pairs;
+  *flags = static_cast<size_t>(rem);
+  *partial_floats = static_cast<size_t>(rem) * (gp.tail_split - 1) * 256 * block_n;
 }
 
 int choose_splits(int num_kb, int want) {
@@ -505,6 +538,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_CONV_MODE")) ctx->conv_mode = atoi(e);
   if (const char* e = getenv("FRB_SLAB")) ctx->use_slab = atoi(e);
   if (const char* e = getenv("FRB_QUAD")) ctx->conv_quad = atoi(e);
+  if (const char* e = getenv("FRB_TAIL_SPLIT")) ctx->tail_split = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
   if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
   if (const char* e = getenv("FRB_MATCH_PAIR")) ctx->match_pair = atoi(e);
@@ -574,7 +608,7 @@ extern "C" void frb_ctx_destroy(frb_ctx* ctx) {
                   ctx->d_flagged, ctx->d_flag_rows, ctx->d_exact, ctx->d_scores64_tmp, ctx->d_stage_u8,
                   ctx->d_stage_in, ctx->d_stage_emb, ctx->d_stage_norm, ctx->d_stage_sc, ctx->d_stage_idx,
                   ctx->d_stage_acc, ctx->d_jobs, ctx->d_progress, ctx->d_seg, ctx->d_sample_identity, ctx->d_id_top_idx,
-                  ctx->d_id_top_sc, ctx->d_id_acc, ctx->d_id_sc32, ctx->d_id_scores};
+                  ctx->d_id_top_sc, ctx->d_id_acc, ctx->d_id_sc32, ctx->d_id_scores, ctx->d_tail_partial, ctx->d_tail_flags};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto* b : ctx->d_bufs)
@@ -771,6 +805,27 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
       pl.grid[i] = std::min(mn_tiles * gp.num_splits, ctx->num_sms);
     }
   }
+  // split-K scratch: one partial area shared by all layers (they run one after the other), one flag region per layer
+  size_t max_partial = 0, total_flags = 0;
+  std::vector<size_t> flag_off(nl, 0);
+  for (size_t i = 0; i < nl; ++i) {
+    if (ctx->layers[i].op != FRB_OP_CONV || pl.use_slab[i]) continue;
+    size_t pf, fl;
+    tail_split_needs(pl.gp[i], pl.block_n[i], pl.grid[i], &pf, &fl);
+    flag_off[i] = total_flags;
+    total_flags += fl;
+    max_partial = std::max(max_partial, pf);
+  }
+  pl.tail_flags = total_flags;
+  if (total_flags > 0) {
+    if (ensure(ctx, &ctx->d_tail_partial, &ctx->tail_partial_cap, max_partial)) return 1;
+    if (ensure(ctx, &ctx->d_tail_flags, &ctx->tail_flags_cap, total_flags)) return 1;
+    for (size_t i = 0; i < nl; ++i)
+      if (ctx->layers[i].op == FRB_OP_CONV && !pl.use_slab[i] && pl.gp[i].tail_split > 1) {
+        pl.gp[i].tail_partial = ctx->d_tail_partial;
+        pl.gp[i].tail_flag = ctx->d_tail_flags + flag_off[i];
+      }
+  }
   return 0;
 }
 
@@ -788,6 +843,7 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
   Plan& pl = ctx->plan;
   const bool dataflow = pl.dataflow && ctx->conv_mode == 2;
   if (dataflow) CK(cudaMemsetAsync(ctx->d_progress, 0, sizeof(int) * Bn, st));
+  if (pl.tail_flags > 0) CK(cudaMemsetAsync(ctx->d_tail_flags, 0, sizeof(int) * pl.tail_flags, st));
   if (ctx->profiling) {
     while (ctx->prof_events.size() < ctx->layers.size() + 1) {
       cudaEvent_t e;
@@ -1489,6 +1545,16 @@ extern "C" int frb_debug_conv(frb_ctx* ctx, const frb_layer_desc* L, int B, cons
     return launch_slab(ctx, LL.cin / 64, a, b, sp, smem_bytes, grid, st);
   }
   if (setup_conv(ctx, LL, B, d_in, d_sc, d_res, d_w, d_bias, d_prelu, d_out, &a, &a2, &b, &gp, &bn, &grid)) return 1;
+  if (gp.tail_split > 1) {
+    size_t pf, fl;
+    tail_split_needs(gp, bn, grid, &pf, &fl);
+    if (ensure(ctx, &ctx->d_tail_partial, &ctx->tail_partial_cap, pf)) return 1;
+    if (ensure(ctx, &ctx->d_tail_flags, &ctx->tail_flags_cap, fl)) return 1;
+    ctx->plan.gp.clear();  // the resident plan's scratch pointers may have moved
+    gp.tail_partial = ctx->d_tail_partial;
+    gp.tail_flag = ctx->d_tail_flags;
+    CK(cudaMemsetAsync(ctx->d_tail_flags, 0, fl * sizeof(int), st));
+  }
   return launch_conv(ctx, bn, a, a2, b, gp, grid, st);
 }
 

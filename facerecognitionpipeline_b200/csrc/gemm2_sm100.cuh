@@ -138,6 +138,41 @@ __device__ __forceinline__ void umma2_commit_mask(uint64_t* bar, uint16_t mask) 
       : "memory");
 }
 
+// Work items of one CTA pair (or quad) in launch order.  Full rounds first: tile = unit + i * units.  Then, when the
+// last round is only partially filled (rem tiles for `units` clusters) and tail_split > 1, those tiles are cut along K:
+// the rem * (split-1) partial producers come first, the rem owners last, so an owner only ever waits for CTAs that
+// never wait themselves (no deadlock with every CTA resident).
+struct TileItem {
+  int tile;       // output tile (m unit * n_tiles + n tile)
+  int kb0, kb1;   // K block range
+  int part;       // -1 = whole K; 0 = owner of a split tile; >= 1 = partial producer
+  int tail_tile;  // index among the split tiles
+};
+__device__ __forceinline__ bool tile_item(int it, int unit, int units, int total_tiles, int num_kb, int split, TileItem* w) {
+  const int full_rounds = total_tiles / units;
+  w->kb0 = 0; w->kb1 = num_kb; w->part = -1; w->tail_tile = 0;
+  if (split <= 1 || it < full_rounds) {
+    w->tile = unit + it * units;
+    return w->tile < total_tiles;
+  }
+  const int rem = total_tiles - full_rounds * units;
+  const int q = unit + (it - full_rounds) * units;
+  const int nprod = rem * (split - 1);
+  if (q >= rem * split) return false;
+  if (q < nprod) {
+    w->tail_tile = q / (split - 1);
+    w->part = 1 + q % (split - 1);
+  } else {
+    w->tail_tile = q - nprod;
+    w->part = 0;
+  }
+  w->tile = full_rounds * units + w->tail_tile;
+  const int per = num_kb / split;
+  w->kb0 = w->part * per;
+  w->kb1 = w->kb0 + per;
+  return true;
+}
+
 constexpr int kGemm2Threads = 320;  // producer warp + MMA warp + 8 epilogue warps
 
 template <int BLOCK_N>
@@ -192,6 +227,7 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int total_tiles = m_units * n_tiles;
   const int first_tile = blockIdx.x / CL;
   const int tile_step = gridDim.x / CL;
+  const int split = (CL == 2) ? p.tail_split : 0;   // split-K of the last partial round (see TileItem)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -240,7 +276,9 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t full_peerbit0 = smem_u32(&full_bar[0]) & 0xFEFFFFFFu;   // multicast form: "even CTA of each destination"
     const uint16_t b_mask = static_cast<uint16_t>((1u << crank) | (1u << (crank + 2)));
     const int pq = p.P * p.Q;
-    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+    TileItem w;
+    for (int it = 0; tile_item(it, first_tile, tile_step, total_tiles, num_kb, split, &w); ++it) {
+      const int tile = w.tile;
       const int n_tile = tile % n_tiles;
       const int m_tile = ((tile / n_tiles) * PAIRS + pair_id) * 2 + crank;
       const int m0 = (m_tile * kBlockM < p.M) ? m_tile * kBlockM : 0;  // padding tile: re-read tile 0, stores masked
@@ -255,8 +293,10 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int m_last = min(m0 + kBlockM, p.M) - 1;
         wait_images(p.progress, img, m_last / pq, p.wait_target);
       }
-      int tap_r = 0, tap_s = 0, cc = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      // a split item starts in the middle of the filter (split tiles have no shortcut K blocks)
+      int cc = w.kb0 % p.cin_chunks;
+      int tap_r = (w.kb0 / p.cin_chunks) / 3, tap_s = (w.kb0 / p.cin_chunks) % 3;
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         {
           const uint32_t full_leader = full_leader0 + 8 * stage;
@@ -306,11 +346,13 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
       const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | static_cast<uint32_t>(desc0);
       const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | static_cast<uint32_t>(desc0);
-      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      TileItem w;
+      for (int it = 0; tile_item(it, first_tile, tile_step, total_tiles, num_kb, split, &w); ++it) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_first = w.kb0, kb_last = w.kb1 - 1;
+        for (int kb = kb_first; kb <= kb_last; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           {
@@ -321,9 +363,9 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k)
-                umma2_bf16_ss_lo(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma2_bf16_ss_lo(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb > kb_first || k > 0) ? 1u : 0u);
               umma2_commit_mask(&empty_bar[stage], static_cast<uint16_t>((1u << CL) - 1));   // one arrival in every CTA of the cluster
-              if (kb == num_kb - 1) umma2_commit_mask(&tmem_full_bar[acc], static_cast<uint16_t>(3u << lead_rank));   // accumulators ready in both CTAs of the pair
+              if (kb == kb_last) umma2_commit_mask(&tmem_full_bar[acc], static_cast<uint16_t>(3u << lead_rank));   // accumulators ready in both CTAs of the pair
             }
           }
           __syncwarp();
@@ -346,7 +388,9 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int epi_tid = threadIdx.x - 64;  // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+    TileItem w;
+    for (int it = 0; tile_item(it, first_tile, tile_step, total_tiles, num_kb, split, &w); ++it) {
+      const int tile = w.tile;
       const int n_tile = tile % n_tiles;
       const int m_tile = ((tile / n_tiles) * PAIRS + pair_id) * 2 + crank;
       const int row = quad * 32 + lane;
@@ -383,6 +427,48 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+      // split tiles: this thread's row of the raw fp32 partial tiles, [tail tile][part-1][256 rows][BLOCK_N]
+      float* part_row = nullptr;
+      if (w.part >= 0)
+        part_row = p.tail_partial + (static_cast<size_t>(w.tail_tile) * (split - 1) * 256 + crank * kBlockM + row) * BLOCK_N;
+      if (w.part > 0) {
+        // ---- partial producer: dump the accumulators, publish, next item
+        float* dst_row = part_row + static_cast<size_t>(w.part - 1) * 256 * BLOCK_N;
+#pragma unroll 1
+        for (int c = half; c < BLOCK_N / 32; c += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          uint4* dst = reinterpret_cast<uint4*>(dst_row + c * 32);
+#pragma unroll
+          if (!(p.tail_debug & 4))
+            for (int j = 0; j < 8; ++j) __stcg(dst + j, make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+        }
+        tc_fence_before();
+        if (!(p.tail_debug & 8)) __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), lead_rank));
+          if (!(p.tail_debug & 8)) atomicAdd(p.tail_flag + w.tail_tile, 1);
+        }
+        if (++acc == S::kAccStages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
+      if (w.part == 0 && !(p.tail_debug & 1)) {
+        // ---- owner: every partial of this tile must be in memory (8 warps x 2 CTAs per producer)
+        const int target = (split - 1) * 16;
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(p.tail_flag + w.tail_tile) < target) {
+          __nanosleep(64);
+          if (++spins > (1u << 24)) {
+            printf("frb: split-K wait timeout block %d tile %d\n", blockIdx.x, tile);
+            __trap();
+          }
+        }
+      }
 #pragma unroll 1
       for (int c = half; c < BLOCK_N / 32; c += 2) {
         uint32_t r[32];
@@ -394,6 +480,19 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int j = 0; j < 4; ++j) rs[j] = __ldg(rp + j);
         }
         tmem_ld_wait();
+        if (w.part == 0 && !(p.tail_debug & 2)) {
+          for (int s2 = 0; s2 < split - 1; ++s2) {
+            const uint4* src = reinterpret_cast<const uint4*>(part_row + static_cast<size_t>(s2) * 256 * BLOCK_N + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 q4 = __ldcg(src + j);
+              r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + __uint_as_float(q4.x));
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + __uint_as_float(q4.y));
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + __uint_as_float(q4.z));
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + __uint_as_float(q4.w));
+            }
+          }
+        }
         if (valid) {
           float v[32];
           const float4* bp = reinterpret_cast<const float4*>(bias_row + c * 32);

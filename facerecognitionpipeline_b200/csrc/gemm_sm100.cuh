@@ -46,6 +46,13 @@ struct GemmParams {
   int* progress;
   int wait_target;
   int sig_fence;  // experiments only: 0 drops the release fence before the progress update (UNSAFE)
+  // split-K for the LAST, partially filled round of tiles (gemm2_sm100_kernel, CL = 2): the `rem` tiles left after the
+  // full rounds are cut into tail_split K ranges; part 0 ("owner") adds the other parts' raw fp32 accumulators
+  // (tail_partial, [rem][tail_split-1][256][BLOCK_N]) before its epilogue, once tail_flag[tile] shows they are stored
+  int tail_split;        // 0/1 = off
+  float* tail_partial;
+  int* tail_flag;        // [rem], zeroed before the launch
+  int tail_debug;        // timing experiments only (wrong results): 1 no wait, 2 no partial loads, 4 no dump, 8 no fence/flag
   int quad;       // host side only: launch gemm2_sm100_kernel<., 4> (two CTA pairs sharing the weight tile by multicast)
 };
 

@@ -15,7 +15,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
-RUNGS = ["gemm", "im2col", "conv", "match"]
+RUNGS = ["gemm", "im2col", "conv", "match", "conv_big"]
 
 
 def _ctx():
@@ -200,6 +200,25 @@ def rung_conv():
     ]
     for i, c in enumerate(cases):
         r = _conv_case(ctx, *c, seed=i)
+        res.append(r)
+        print(r, flush=True)
+    return res
+
+
+def rung_conv_big():
+    """Full-batch shapes whose last round of tiles is partial: exercises FRB_TAIL_SPLIT (split-K tail) and FRB_QUAD."""
+    ctx = _ctx()
+    res = []
+    cases = [
+        (256, 14, 14, 256, 256, 3, 1, 9, True, 0, 0),     # 196 tiles on 74 pairs: 48 tail tiles x 3
+        (256, 14, 14, 256, 256, 3, 1, 1, False, 1, 0),
+        (200, 14, 14, 256, 256, 3, 1, 9, True, 1, 0),     # 154 tiles: 6 tail tiles
+        (256, 7, 7, 512, 512, 3, 1, 9, True, 0, 0),       # two N tiles, 24 tail tiles
+        (64, 28, 28, 128, 256, 3, 1, 9, True, 0, 0),      # 196 tiles, K = 18 blocks
+        (250, 14, 14, 256, 512, 3, 1, 9, True, 0, 0),     # M not a multiple of 256 + two N tiles
+    ]
+    for i, c in enumerate(cases):
+        r = _conv_case(ctx, *c, seed=100 + i)
         res.append(r)
         print(r, flush=True)
     return res
