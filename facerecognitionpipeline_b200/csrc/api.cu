@@ -979,7 +979,7 @@ extern "C" int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, lon
     if (ctx->d_gal_bf16) CK(cudaFree(ctx->d_gal_bf16));
     ctx->d_gal = nullptr;
     ctx->d_gal_bf16 = nullptr;
-    const long long cap = std::max<long long>(N, 256);
+    const long long cap = (std::max<long long>(N, 256) + 255) / 256 * 256;  // whole 128-row groups (K-blocked bf16 copy)
     CK(cudaMalloc(&ctx->d_gal, static_cast<size_t>(cap) * 512 * 4));
     CK(cudaMalloc(&ctx->d_gal_bf16, static_cast<size_t>(cap) * 512 * 2));
     ctx->gal_cap = cap;
@@ -990,12 +990,14 @@ extern "C" int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, lon
   CK(cudaMemset(ctx->d_gal_maxnorm, 0, 4));
   if (N == 0) return 0;
   CK(cudaMemcpy(ctx->d_gal, g, static_cast<size_t>(N) * 512 * 4, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
-  gallery_prepare_kernel<<<static_cast<unsigned>((N + 7) / 8), 256>>>(ctx->d_gal, N, ctx->d_gal_bf16, ctx->d_gal_maxnorm);
+  const long long groups = (N + kGalGroup - 1) / kGalGroup;
+  gallery_prepare_kernel<<<static_cast<unsigned>(groups * kGalGroup / 8), 256>>>(ctx->d_gal, N, ctx->d_gal_bf16, ctx->d_gal_maxnorm);
   CK(cudaGetLastError());
   ctx->launches++;
   CK(cudaDeviceSynchronize());
-  if (make_tmap_2d(ctx, &ctx->tmG, ctx->d_gal_bf16, 512, static_cast<uint64_t>(N), kMatchBN)) return 1;
-  if (make_tmap_2d(ctx, &ctx->tmG2, ctx->d_gal_bf16, 512, static_cast<uint64_t>(N), kMatchBN / 2)) return 1;
+  // K-blocked copy as a [groups * 8 * 128][64] tensor: one box = one K block of one 128-row group = 16 KB contiguous
+  if (make_tmap_2d(ctx, &ctx->tmG2, ctx->d_gal_bf16, 64, static_cast<uint64_t>(groups) * kMatchKB * kGalGroup, kGalGroup)) return 1;
+  ctx->tmG = ctx->tmG2;
   return 0;
 }
 

@@ -24,6 +24,12 @@ constexpr int kCand = 8;                // candidates kept per (probe, slice)
 constexpr int kMatchBStages = 3;
 constexpr int kMatchThreads = 192;
 
+// bf16 gallery copy, K-blocked: rows are grouped by kGalGroup = 128; K block kb (64 columns) of group g is ONE
+// contiguous 16 KB box at box-row (g * 8 + kb) * 128 of a [groups * 8 * 128][64] tensor, so every TMA stage of the
+// filter streams a contiguous piece of HBM (a row-major copy made each box 128 pieces of 128 B, 1 KB apart).
+constexpr int kGalGroup = 128;
+__host__ __device__ __forceinline__ int gallery_box_row(int group, int kb) { return (group * kMatchKB + kb) * kGalGroup; }
+
 struct MatchParams {
   int P;                 // probes
   long long N;           // gallery rows held by this rank
@@ -156,7 +162,10 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
           mbar_wait(&b_empty[stage], phase ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&b_full[stage], S::kBBytes);
-            tma_load_2d(&tmG, &b_full[stage], smem_b + stage * S::kBBytes, kb * 64, t * kMatchBN);
+            // K-blocked gallery copy (gallery_prepare_kernel): a 256-row tile is two 128-row groups, each K block of a
+            // group one contiguous 16 KB box
+            tma_load_2d(&tmG, &b_full[stage], smem_b + stage * S::kBBytes, 0, gallery_box_row(2 * t, kb));
+            tma_load_2d(&tmG, &b_full[stage], smem_b + stage * S::kBBytes + S::kBBytes / 2, 0, gallery_box_row(2 * t + 1, kb));
           }
           __syncwarp();
           if (++stage == kMatchBStages) {
@@ -371,8 +380,7 @@ match_filter2_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
           mbar_wait(&b_empty[stage], phase ^ 1);
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * S::kBBytes);
-            tma2_load_2d(&tmG2, b_full_leader0 + 8 * stage, smem_b + stage * S::kBBytes, kb * 64,
-                         t * kMatchBN + crank * (kMatchBN / 2));
+            tma2_load_2d(&tmG2, b_full_leader0 + 8 * stage, smem_b + stage * S::kBBytes, 0, gallery_box_row(2 * t + crank, kb));
           }
           __syncwarp();
           if (++stage == kMatch2BStages) {

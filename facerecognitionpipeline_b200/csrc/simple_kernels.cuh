@@ -420,31 +420,31 @@ probe_prepare_kernel(const float* __restrict__ in, int normalize, float* __restr
   }
 }
 
-// fp32 gallery rows -> bf16 copy + per-block max row norm (for the filter's error bound)
+// fp32 gallery rows -> K-blocked bf16 copy (match_sm100.cuh: gallery_box_row) + max row norm (for the filter's error
+// bound).  The grid covers whole 128-row groups: rows >= N are written as zeros.
 __global__ void __launch_bounds__(256)
 gallery_prepare_kernel(const float* __restrict__ g, long long N, __nv_bfloat16* __restrict__ gb,
                        float* __restrict__ max_norm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
-  float nrm = 0.f;
-  if (row < N) {
-    const float4* src = reinterpret_cast<const float4*>(g + row * 512);
-    uint2* dst = reinterpret_cast<uint2*>(gb + row * 512);
-    float ss = 0.f;
+  const long long group = row >> 7;
+  const int r = static_cast<int>(row & 127);
+  float ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 v = src[lane + 32 * j];
-      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-      uint2 o;
-      o.x = pack_bf16x2(v.x, v.y);
-      o.y = pack_bf16x2(v.z, v.w);
-      dst[lane + 32 * j] = o;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    nrm = sqrtf(ss);
+  for (int j = 0; j < 4; ++j) {
+    const int col = 4 * (lane + 32 * j);          // this lane's 4 columns
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < N) v = reinterpret_cast<const float4*>(g + row * 512)[lane + 32 * j];
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    const size_t box_row = static_cast<size_t>(group * 8 + (col >> 6)) * 128 + r;
+    *reinterpret_cast<uint2*>(gb + box_row * 64 + (col & 63)) = o;
   }
-  if (lane == 0 && row < N) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(nrm));  // nrm >= 0
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0 && row < N) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(sqrtf(ss)));  // norm >= 0
 }
 
 // ------------------------------------------------------------------ exact scoring helpers
@@ -526,6 +526,71 @@ match_finalize_kernel(const FinalizeParams p) {
     __syncthreads();
     if (t == 0) s_excl = fmaxf(fmaxf(s_mx[0], s_mx[1]), fmaxf(s_mx[2], s_mx[3]));
     __syncthreads();
+  }
+  // Only the best kRescore candidates (and the next one, for the bound) matter.  With many slices, first cut the
+  // list down to its ~128 best by bisection on the ordered-integer image of the scores (32 counting passes), then
+  // sort 256 entries instead of up to 2048 (the full sort was 75 us per launch at P = 256: profiles/r01c).  Massive
+  // ties at the cut (more than 256 entries at or above it) keep the full sort.
+  if (Cp > 256) {
+    __shared__ int s_w[4];
+    __shared__ int s_fill;
+    unsigned keys[kMaxCandPad / 128];
+    const int per = Cp / 128;
+#pragma unroll
+    for (int u = 0; u < kMaxCandPad / 128; ++u) {
+      keys[u] = 0u;
+      if (u < per) {
+        const int i = t + u * 128;
+        if (s_ix[i] >= 0) {
+          const unsigned b = __float_as_uint(s_sc[i]);
+          keys[u] = (b & 0x80000000u) ? ~b : (b | 0x80000000u);   // order-preserving; 0 = empty slot
+          if (keys[u] == 0u) keys[u] = 1u;
+        }
+      }
+    }
+    auto count_ge = [&](unsigned thr_key) {
+      int c = 0;
+#pragma unroll
+      for (int u = 0; u < kMaxCandPad / 128; ++u) c += (keys[u] >= thr_key) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) s_w[warp] = c;
+      __syncthreads();
+      const int total = s_w[0] + s_w[1] + s_w[2] + s_w[3];
+      __syncthreads();
+      return total;
+    };
+    const int valid = count_ge(1u);
+    const int want = valid < 128 ? valid : 128;
+    unsigned lo = 1u, hi = 0xFFFFFFFFu;      // largest key threshold that still keeps `want` candidates
+    while (lo < hi) {
+      const unsigned mid = lo + (hi - lo + 1u) / 2u;
+      if (count_ge(mid) >= want) lo = mid; else hi = mid - 1u;
+    }
+    const int kept = count_ge(lo);
+    if (want > 0 && kept <= 256) {
+      __shared__ float s_sc2[256];
+      __shared__ int s_ix2[256];
+      if (t == 0) s_fill = 0;
+      for (int i = t; i < 256; i += 128) {
+        s_sc2[i] = -INFINITY;
+        s_ix2[i] = -1;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < kMaxCandPad / 128; ++u)
+        if (u < per && keys[u] >= lo) {
+          const int slot = atomicAdd(&s_fill, 1);
+          s_sc2[slot] = s_sc[t + u * 128];
+          s_ix2[slot] = s_ix[t + u * 128];
+        }
+      __syncthreads();
+      for (int i = t; i < 256; i += 128) {
+        s_sc[i] = s_sc2[i];
+        s_ix[i] = s_ix2[i];
+      }
+      Cp = 256;
+      __syncthreads();
+    }
   }
   // bitonic sort of the approximate candidates, canonical order
   for (int k2 = 2; k2 <= Cp; k2 <<= 1) {
