@@ -26,6 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "aligned faces/sec embedded+matched (IR-101, 1M gallery)"
+# dram__bytes_read.sum + dram__bytes_write.sum of the persistent 66-layer run at batch 256 (ncu --set full, profiles/r01d_summary.md)
+RUN_TRAFFIC = None
 UNIT = "faces/s"
 
 
@@ -308,7 +310,8 @@ def run_ours(args):
     # its launches / their summed duration).  Event-separated launches do not overlap, so this is per-launch time.
     KNAMES = {0: "stem_tc_kernel", 1: "gemm2_sm100_kernel<64>", 2: "gemm2_sm100_kernel<128>", 3: "gemm2_sm100_kernel<256>",
               4: "conv_slab_sm100_kernel<64,1>", 5: "conv_slab_sm100_kernel<128,1>", 6: "conv_slab_sm100_kernel<128,2>",
-              7: "gemm_sm100_kernel<256,0,1> + fc_finalize_kernel"}
+              7: "gemm_sm100_kernel<256,0,1> + fc_finalize_kernel",
+              8: "gemm2_multi_sm100_kernel<256> (persistent run of consecutive conv layers, one launch)"}
     MAXL = 256
     ms = (C.c_float * MAXL)(); kid = (C.c_int * MAXL)(); fl = (C.c_double * MAXL)(); nl = C.c_int(0)
     per_kernel = {}
@@ -319,8 +322,9 @@ def run_ours(args):
         if i == 0:
             continue  # first profiled step creates the events
         for j in range(nl.value):
-            acc = per_kernel.setdefault(kid[j], [0, 0.0, 0.0])
-            acc[0] += 1; acc[1] += ms[j]; acc[2] += fl[j]
+            acc = per_kernel.setdefault(abs(kid[j]), [0, 0.0, 0.0])
+            acc[0] += 1 if kid[j] >= 0 else 0        # a negative id continues the launch reported before it
+            acc[1] += ms[j]; acc[2] += fl[j]
     dom = max(per_kernel, key=lambda k: per_kernel[k][1])
     n_l, ms_sum, fl_sum = per_kernel[dom]
     total_prof_ms = sum(v[1] for v in per_kernel.values())
@@ -328,7 +332,7 @@ def run_ours(args):
     section_tf = flops_face * B / (embed_ms / 1e3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that kernel from the committed `ncu --set full`
     # capture (profiles/r01b_summary.md); null when the dominant kernel is not the one that was captured
-    traffic = {3: 26.94e6, 6: 57.30e6}.get(dom)
+    traffic = {3: 26.94e6, 6: 57.30e6, 8: RUN_TRAFFIC}.get(dom)
     roofline = dict(bound="tensor", achieved=dom_tf, peak=peaks["tf_sustained"], unit="TFLOP/s",
                     frac=dom_tf / peaks["tf_sustained"], traffic=traffic, kernel=KNAMES[dom],
                     launches_per_step=n_l // PROF_STEPS, avg_launch_us=ms_sum / n_l * 1e3,

@@ -16,6 +16,7 @@
 #include "../../include/frb200.h"
 #include "gemm_sm100.cuh"
 #include "gemm2_sm100.cuh"
+#include "gemm2_multi_sm100.cuh"
 #include "conv_slab_sm100.cuh"
 #include "match_sm100.cuh"
 #include "stem_sm100.cuh"
@@ -35,6 +36,11 @@ struct Plan {  // per-batch-size launch plan of the backbone
   std::vector<GemmParams> gp;
   std::vector<int> block_n, grid;
   size_t tail_flags = 0;           // split-K flags of all layers (zeroed at the start of every embed)
+  // persistent runs (gemm2_multi_sm100_kernel): run_len[i] > 1 = layers i .. i+run_len[i]-1 go out as ONE launch
+  std::vector<int> run_len, run_grid, run_index;
+  int num_runs = 0;
+  size_t run_layers = 0;           // layers in all runs = grid-barrier counters (zeroed at the start of every embed)
+  std::vector<size_t> run_off;     // offset of the run's first Gemm2Layer in ctx->d_runs
   std::vector<int> use_slab;       // 1 = conv_slab_sm100_kernel (3x3 stride-1, W in {28,56,112})
   std::vector<SlabParams> sp;
   std::vector<int> slab_smem;
@@ -56,6 +62,11 @@ struct frb_ctx {
   int tail_split = 0;  // FRB_TAIL_SPLIT=1: split-K for the last partial round of the pair conv kernel (see TileItem)
   float* d_tail_partial = nullptr; size_t tail_partial_cap = 0;
   int* d_tail_flags = nullptr; size_t tail_flags_cap = 0;
+  int multi_coop = 1;  // FRB_MULTI_COOP=0: no cooperative-launch attribute on the persistent run kernel
+  int conv_multi = 2;  // persistent multi-layer runs of the pair conv kernel: 2 = per-image dataflow between the run's
+                       // layers (default), 1 = grid barrier between them, 0 = every conv layer is a launch of its own
+  Gemm2Layer* d_runs = nullptr; size_t runs_cap = 0;
+  int* d_run_bar = nullptr; size_t run_bar_cap = 0;
   int conv_quad = 0;  // FRB_QUAD: gemm2_sm100_kernel<., 4> for Cout >= 256 (1) / >= 128 (2) layers
   int quad_clusters = 0;
   int use_slab = 1;   // activation-slab kernel for eligible 3x3 stride-1 layers (FRB_SLAB=0 disables)
@@ -312,6 +323,58 @@ int launch_conv(frb_ctx* ctx, int block_n, const CUtensorMap& a, const CUtensorM
   return fail(ctx, "unsupported conv block_n=%d", block_n);
 }
 
+// One persistent launch for a run of consecutive CTA-pair conv layers (gemm2_multi_sm100.cuh).
+template <int BN>
+int launch_gemm2_multi_t(frb_ctx* ctx, const Gemm2Layer* d_layers, int n, int* d_bar, int grid, cudaStream_t st) {
+  auto kern = gemm2_multi_sm100_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::kTotal));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemm2Threads);
+  cfg.dynamicSmemBytes = Gemm2Smem<BN>::kTotal;
+  cfg.stream = st;
+  // The layers of a run wait for each other inside the kernel, so every CTA must be resident at the same time.
+  // grid <= number of SMs with one CTA per SM gives that on an otherwise idle GPU; the cooperative attribute makes
+  // the driver guarantee it (gang scheduling) even when other work shares the device.
+  cudaLaunchAttribute base[2], attr[3];
+  fill_launch_attrs(base, 2);   // [0] cluster dimension, [1] programmatic stream serialization
+  auto launch = [&](bool pdl) {
+    int na = 0;
+    attr[na++] = base[0];
+    if (pdl) attr[na++] = base[1];
+    if (ctx->multi_coop) {
+      attr[na].id = cudaLaunchAttributeCooperative;
+      attr[na].val.cooperative = 1;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kern, d_layers, n, d_bar);
+  };
+  const bool pdl = ctx->use_pdl && ctx->multi_coop != 2;
+  cudaError_t e = launch(pdl);
+  if (e != cudaSuccess && ctx->multi_coop && pdl) {
+    // cooperative + programmatic serialization refused by this driver: keep the co-residency guarantee, drop the overlap
+    cudaGetLastError();
+    e = launch(false);
+    if (e == cudaSuccess) ctx->multi_coop = 2;
+  }
+  CK(e);
+  ctx->launches++;
+  return 0;
+}
+
+int launch_gemm2_multi(frb_ctx* ctx, int block_n, const Gemm2Layer* d_layers, int n, int* d_bar, int grid, cudaStream_t st) {
+  if (block_n == 64) return launch_gemm2_multi_t<64>(ctx, d_layers, n, d_bar, grid, st);
+  if (block_n == 128) return launch_gemm2_multi_t<128>(ctx, d_layers, n, d_bar, grid, st);
+  if (block_n == 256) return launch_gemm2_multi_t<256>(ctx, d_layers, n, d_bar, grid, st);
+  return fail(ctx, "unsupported multi-layer conv block_n=%d", block_n);
+}
+
 // NHWC bf16 activation [N][H][W][C] as a tiled 4-D tensor; box = 64 channels x box_w x box_h x 1 image.
 int make_tmap_4d_tiled(frb_ctx* ctx, CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int box_w, int box_h) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -538,6 +601,8 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_CONV_MODE")) ctx->conv_mode = atoi(e);
   if (const char* e = getenv("FRB_SLAB")) ctx->use_slab = atoi(e);
   if (const char* e = getenv("FRB_QUAD")) ctx->conv_quad = atoi(e);
+  if (const char* e = getenv("FRB_MULTI")) ctx->conv_multi = atoi(e);
+  if (const char* e = getenv("FRB_MULTI_COOP")) ctx->multi_coop = atoi(e);
   if (const char* e = getenv("FRB_TAIL_SPLIT")) ctx->tail_split = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
   if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
@@ -608,7 +673,7 @@ extern "C" void frb_ctx_destroy(frb_ctx* ctx) {
                   ctx->d_flagged, ctx->d_flag_rows, ctx->d_exact, ctx->d_scores64_tmp, ctx->d_stage_u8,
                   ctx->d_stage_in, ctx->d_stage_emb, ctx->d_stage_norm, ctx->d_stage_sc, ctx->d_stage_idx,
                   ctx->d_stage_acc, ctx->d_jobs, ctx->d_progress, ctx->d_seg, ctx->d_sample_identity, ctx->d_id_top_idx,
-                  ctx->d_id_top_sc, ctx->d_id_acc, ctx->d_id_sc32, ctx->d_id_scores, ctx->d_tail_partial, ctx->d_tail_flags};
+                  ctx->d_id_top_sc, ctx->d_id_acc, ctx->d_id_sc32, ctx->d_id_scores, ctx->d_tail_partial, ctx->d_tail_flags, ctx->d_runs, ctx->d_run_bar};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto* b : ctx->d_bufs)
@@ -816,6 +881,51 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
     total_flags += fl;
     max_partial = std::max(max_partial, pf);
   }
+  // persistent runs: maximal sequences of consecutive pair-kernel conv layers with the same Cout tile
+  pl.run_len.assign(nl, 0); pl.run_grid.assign(nl, 0); pl.run_index.assign(nl, -1); pl.run_off.assign(nl, 0);
+  pl.num_runs = 0;
+  if (ctx->conv_multi && ctx->conv_mode == 2 && !ctx->use_dataflow && ctx->num_sms >= 2) {
+    auto eligible = [&](size_t i) {
+      return ctx->layers[i].op == FRB_OP_CONV && !pl.use_slab[i] && !pl.gp[i].quad && pl.gp[i].tail_split <= 1 &&
+             pl.grid[i] <= ctx->num_sms;
+    };
+    std::vector<Gemm2Layer> host;
+    size_t i = 0;
+    while (i < nl) {
+      if (!eligible(i)) { ++i; continue; }
+      size_t j = i + 1;
+      const size_t max_run = getenv("FRB_MULTI_MAXRUN") ? static_cast<size_t>(atoi(getenv("FRB_MULTI_MAXRUN"))) : nl;
+      while (j < nl && j - i < max_run && eligible(j) && pl.block_n[j] == pl.block_n[i]) ++j;
+      if (j - i >= 2) {
+        pl.run_len[i] = static_cast<int>(j - i);
+        pl.run_index[i] = pl.num_runs++;
+        pl.run_off[i] = host.size();
+        int g = 0;
+        long long units = 0;   // run-local progress units per image written by the run's layers so far
+        for (size_t q = i; q < j; ++q) {
+          g = std::max(g, pl.grid[q]);
+          Gemm2Layer gl;
+          gl.tmA = pl.tmA[q]; gl.tmA2 = pl.tmA2[q]; gl.tmB = pl.tmB[q]; gl.p = pl.gp[q];
+          if (ctx->conv_multi >= 2) {   // dataflow inside the run (FRB_MULTI=2): per-image progress instead of grid barriers
+            gl.p.progress = ctx->d_progress;
+            gl.p.wait_target = static_cast<int>(units);
+            gl.p.sig_fence = 1;
+            units += static_cast<long long>(gl.p.P) * gl.p.Q * (gl.p.N / 32);
+          }
+          if (const char* e = getenv("FRB_MULTI_DEBUG")) gl.p.tail_debug = atoi(e);
+          host.push_back(gl);
+        }
+        pl.run_grid[i] = g;
+      }
+      i = j;
+    }
+    if (pl.num_runs > 0) {
+      if (ensure(ctx, &ctx->d_runs, &ctx->runs_cap, host.size())) return 1;
+      if (ensure(ctx, &ctx->d_run_bar, &ctx->run_bar_cap, host.size())) return 1;   // one barrier counter per layer
+      pl.run_layers = host.size();
+      CK(cudaMemcpy(ctx->d_runs, host.data(), host.size() * sizeof(Gemm2Layer), cudaMemcpyHostToDevice));
+    }
+  }
   pl.tail_flags = total_flags;
   if (total_flags > 0) {
     if (ensure(ctx, &ctx->d_tail_partial, &ctx->tail_partial_cap, max_partial)) return 1;
@@ -844,6 +954,8 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
   const bool dataflow = pl.dataflow && ctx->conv_mode == 2;
   if (dataflow) CK(cudaMemsetAsync(ctx->d_progress, 0, sizeof(int) * Bn, st));
   if (pl.tail_flags > 0) CK(cudaMemsetAsync(ctx->d_tail_flags, 0, sizeof(int) * pl.tail_flags, st));
+  if (pl.num_runs > 0) CK(cudaMemsetAsync(ctx->d_run_bar, 0, sizeof(int) * pl.run_layers, st));
+  size_t run_end = 0;  // layers below this index were covered by a persistent run launch
   if (ctx->profiling) {
     while (ctx->prof_events.size() < ctx->layers.size() + 1) {
       cudaEvent_t e;
@@ -856,6 +968,15 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
     const frb_layer_desc& L = ctx->layers[i];
     const uint8_t* blob = ctx->d_blob;
     if (ctx->profiling && i > 0) CK(cudaEventRecord(ctx->prof_events[i], st));
+    if (i < run_end) continue;
+    if (pl.run_len[i] > 1) {
+      if (ctx->conv_multi >= 2) CK(cudaMemsetAsync(ctx->d_progress, 0, sizeof(int) * Bn, st));  // run-local progress
+      if (launch_gemm2_multi(ctx, pl.block_n[i], ctx->d_runs + pl.run_off[i], pl.run_len[i], ctx->d_run_bar + pl.run_off[i],
+                             pl.run_grid[i], st))
+        return 1;
+      run_end = i + pl.run_len[i];
+      continue;
+    }
     if (L.op == FRB_OP_STEM) {
       const void* in = L.in_buf < 0 ? d_in : ctx->d_bufs[L.in_buf];
       static bool attr_set = false;
@@ -921,7 +1042,9 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
 
 // Profiling variant of frb_embed: the same launches with a CUDA event between consecutive layers (which also
 // serialises them: no programmatic overlap), so per-layer durations can be read back.  kernel_id: 0 stem,
-// 1/2/3 = CTA-pair im2col conv with Cout tile 64/128/256, 4/5/6 = slab conv <64,1>/<128,1>/<128,2>, 7 = FC + finalize.
+// 1/2/3 = CTA-pair im2col conv with Cout tile 64/128/256, 4/5/6 = slab conv <64,1>/<128,1>/<128,2>, 7 = FC + finalize,
+// 8 = layer of a persistent multi-layer run (gemm2_multi_sm100_kernel): the whole run's time is reported on its first
+// layer, the following layers of the run are reported with id -8 and ~0 ms.
 extern "C" int frb_embed_profile(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, void* stream,
                                  float* h_layer_ms, int* h_kernel_id, double* h_layer_flops, int max_layers,
                                  int* n_layers) {
@@ -949,6 +1072,12 @@ extern "C" int frb_embed_profile(frb_ctx* ctx, const void* d_in, int B, int flag
       if (ctx->plan.use_slab[i]) id = L.cout == 64 ? 4 : (L.cin == 64 ? 5 : 6);
       else id = ctx->plan.block_n[i] == 64 ? 1 : (ctx->plan.block_n[i] == 128 ? 2 : 3);
     }
+    // layers inside a persistent run: the run's time is on its first layer (the others follow it without a gap)
+    for (int q = i; q >= 0; --q)
+      if (ctx->plan.run_len[q] > 1) {
+        if (q + ctx->plan.run_len[q] > i) id = (q == i) ? 8 : -8;   // -8: continuation, not a launch of its own
+        break;
+      }
     if (h_kernel_id) h_kernel_id[i] = id;
     const int P = out_dim(L.hin, L.ksize, L.stride, L.pad), Q = out_dim(L.win, L.ksize, L.stride, L.pad);
     double fl = L.op == FRB_OP_FC ? 2.0 * L.cin * L.cout

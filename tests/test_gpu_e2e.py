@@ -128,9 +128,11 @@ def test_config4_warp_embed_match_stream(ctx):
 
 
 def test_launch_schedules_are_bit_identical(tmp_path):
-    """The three launch schedules of the backbone — plain stream order (FRB_PDL=0), programmatic dependent
-    launch (default) and per-image dataflow counters (FRB_DATAFLOW=1, layers overlap across launch boundaries)
-    — must produce bit-identical embeddings: they only change WHEN a tile runs, never what it computes."""
+    """The launch schedules of the backbone — the default (persistent multi-layer run of the 14x14 / 7x7 layers with
+    per-image dataflow between its layers, FRB_MULTI=2), the same run with grid barriers (FRB_MULTI=1), one launch
+    per layer with programmatic dependent launch (FRB_MULTI=0), plain stream order (FRB_PDL=0) and per-image dataflow
+    across launches (FRB_DATAFLOW=1) — must produce bit-identical embeddings: they only change WHEN a tile runs,
+    never what it computes."""
     import os
     import subprocess
     import sys
@@ -146,8 +148,11 @@ def test_launch_schedules_are_bit_identical(tmp_path):
         "for _ in range(3): e = fe.extract_embeddings_batch(crops)\n"
         "np.save(sys.argv[1], e)\n")
     outs = []
-    for name, env in (("plain", {"FRB_PDL": "0"}), ("pdl", {}), ("dataflow", {"FRB_DATAFLOW": "1"})):
+    for name, env in (("plain", {"FRB_PDL": "0", "FRB_MULTI": "0"}), ("pdl", {"FRB_MULTI": "0"}), ("default", {}),
+                      ("run_barrier", {"FRB_MULTI": "1"}), ("run_flow_plain", {"FRB_MULTI": "2", "FRB_PDL": "0"}),
+                      ("dataflow", {"FRB_DATAFLOW": "1"})):
         out = tmp_path / f"{name}.npy"
         subprocess.run([sys.executable, str(script), str(out)], check=True, env={**os.environ, **env}, timeout=600)
         outs.append(np.load(out))
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
