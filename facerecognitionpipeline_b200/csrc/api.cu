@@ -355,14 +355,11 @@ int launch_gemm2_multi_t(frb_ctx* ctx, const Gemm2Layer* d_layers, int n, int* d
     cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, d_layers, n, d_bar);
   };
-  const bool pdl = ctx->use_pdl && ctx->multi_coop != 2;
+  // A cooperative launch is never combined with programmatic stream serialization here: the run's first layer must
+  // see the previous kernel's output, and the two attributes together produced wrong first-layer inputs at batch 1024
+  // (griddepcontrol.wait did not hold the cooperative grid back).  One plain stream dependency per embed costs nothing.
+  const bool pdl = ctx->use_pdl && (!ctx->multi_coop || getenv("FRB_MULTI_COOP_PDL") != nullptr);
   cudaError_t e = launch(pdl);
-  if (e != cudaSuccess && ctx->multi_coop && pdl) {
-    // cooperative + programmatic serialization refused by this driver: keep the co-residency guarantee, drop the overlap
-    cudaGetLastError();
-    e = launch(false);
-    if (e == cudaSuccess) ctx->multi_coop = 2;
-  }
   CK(e);
   ctx->launches++;
   return 0;
@@ -902,6 +899,7 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
         pl.run_off[i] = host.size();
         int g = 0;
         long long units = 0;   // run-local progress units per image written by the run's layers so far
+        std::vector<std::pair<const void*, long long>> out_layout;   // output buffer -> elements per image at its last write
         for (size_t q = i; q < j; ++q) {
           g = std::max(g, pl.grid[q]);
           Gemm2Layer gl;
@@ -911,10 +909,26 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
             gl.p.wait_target = static_cast<int>(units);
             gl.p.sig_fence = 1;
             units += static_cast<long long>(gl.p.P) * gl.p.Q * (gl.p.N / 32);
+            // stage transitions: the output buffer is re-used with another per-image size -> full wait (see kernel)
+            const long long per_image = static_cast<long long>(gl.p.P) * gl.p.Q * gl.p.N;
+            bool seen = false;
+            for (auto& ol : out_layout)
+              if (ol.first == gl.p.out) {
+                seen = true;
+                if (ol.second != per_image) gl.p.full_wait = 1;
+                ol.second = per_image;
+              }
+            // first write of the run into this buffer: its old content has whatever layout the layers before the run
+            // (or an earlier layer's INPUT view) used - treat as a change unless it is the run's first layer
+            if (!seen) {
+              out_layout.push_back({gl.p.out, per_image});
+              if (q > i) gl.p.full_wait = 1;
+            }
           }
           if (const char* e = getenv("FRB_MULTI_DEBUG")) gl.p.tail_debug = atoi(e);
           host.push_back(gl);
         }
+        if (const char* e = getenv("FRB_MULTI_GRID")) g = std::min(g, std::max(2, atoi(e) & ~1));  // experiments: fewer SMs
         pl.run_grid[i] = g;
       }
       i = j;

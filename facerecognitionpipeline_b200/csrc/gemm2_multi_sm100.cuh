@@ -115,7 +115,14 @@ gemm2_multi_sm100_kernel(const Gemm2Layer* __restrict__ layers, int num_layers, 
         fence_proxy_async_global();  // order the TMA reads below after the acquire
       }
       const int tile0 = flow ? (first_tile + tile_step - rot) % tile_step : first_tile;
-      if (flow) rot = (rot + total_tiles) % tile_step;
+      if (flow && !(p.tail_debug & 4)) rot = (rot + total_tiles) % tile_step;
+      if (flow && l > 0 && p.full_wait && tile0 < total_tiles) {
+        // The image-local argument below needs image i to occupy the same bytes of a buffer every time the buffer is
+        // written.  Where the per-image size of the output buffer changes (stage transitions: 28x28x256 -> 14x14x256,
+        // 14x14x256 -> 14x14x512 -> 7x7x512), image i of the new layout overlaps OTHER images of the old one, so this
+        // layer may only start writing when every earlier layer has finished every image.
+        wait_images(p.progress, 0, p.M / pq - 1, p.wait_target);
+      }
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int n_tile = tile % n_tiles;
         const int m_tile = (tile / n_tiles) * 2 + crank;
@@ -134,6 +141,12 @@ gemm2_multi_sm100_kernel(const Gemm2Layer* __restrict__ layers, int num_layers, 
           // that runs out of tiles in layer l simply continues with layer l+1: no drain, no partial last round.
           const int m_last = min(m0 + kBlockM, p.M) - 1;
           wait_images(p.progress, img, m_last / pq, p.wait_target);
+          if (p.tail_debug & 16) {
+            __syncwarp();
+            (void)ld_acquire_gpu(p.progress + img);
+            fence_proxy_async_global();
+            __nanosleep(2000);
+          }
         }
         int tap_r = 0, tap_s = 0, cc = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -189,7 +202,7 @@ gemm2_multi_sm100_kernel(const Gemm2Layer* __restrict__ layers, int num_layers, 
         const int total_tiles = (((p.M + kBlockM - 1) / kBlockM + 1) / 2) * (p.N / BLOCK_N);
         const bool flow = p.progress != nullptr;
         const int tile0 = flow ? (first_tile + tile_step - rot) % tile_step : first_tile;
-        if (flow) rot = (rot + total_tiles) % tile_step;
+        if (flow && !(p.tail_debug & 4)) rot = (rot + total_tiles) % tile_step;
         for (int tile = tile0; tile < total_tiles; tile += tile_step) {
           mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
@@ -234,7 +247,7 @@ gemm2_multi_sm100_kernel(const Gemm2Layer* __restrict__ layers, int num_layers, 
       const int n_tiles = p.N / BLOCK_N;
       const int total_tiles = (((p.M + kBlockM - 1) / kBlockM + 1) / 2) * n_tiles;
       const int tile0 = (p.progress != nullptr) ? (first_tile + tile_step - rot) % tile_step : first_tile;
-      if (p.progress != nullptr) rot = (rot + total_tiles) % tile_step;
+      if (p.progress != nullptr && !(p.tail_debug & 4)) rot = (rot + total_tiles) % tile_step;
       // this layer's epilogue constants (the previous layer's readers are past the barrier at its end)
       if (p.progress != nullptr && l > 0) asm volatile("bar.sync 1, 256;" ::: "memory");  // flow mode has no end-of-layer barrier
       if (p.N == BLOCK_N) {
@@ -340,7 +353,10 @@ gemm2_multi_sm100_kernel(const Gemm2Layer* __restrict__ layers, int num_layers, 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
-        if (p.progress != nullptr && l + 1 < num_layers) signal_rows(p.progress, valid, img, BLOCK_N / 64, true);
+        if (p.progress != nullptr && l + 1 < num_layers) {
+          if (p.tail_debug & 8) __threadfence();
+          signal_rows(p.progress, valid, img, BLOCK_N / 64, true);
+        }
         if (++acc == S::kAccStages) {
           acc = 0;
           acc_phase ^= 1;

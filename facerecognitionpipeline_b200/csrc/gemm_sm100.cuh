@@ -53,6 +53,8 @@ struct GemmParams {
   float* tail_partial;
   int* tail_flag;        // [rem], zeroed before the launch
   int tail_debug;        // timing experiments only (wrong results): 1 no wait, 2 no partial loads, 4 no dump, 8 no fence/flag
+  int full_wait;  // persistent runs in flow mode: this layer's output buffer changes its per-image layout (stage
+                  // transition), so image-local dependencies do not cover the write-after-read side: wait for ALL images
   int quad;       // host side only: launch gemm2_sm100_kernel<., 4> (two CTA pairs sharing the weight tile by multicast)
 };
 
