@@ -26,8 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "aligned faces/sec embedded+matched (IR-101, 1M gallery)"
-# dram__bytes_read.sum + dram__bytes_write.sum of the persistent 66-layer run at batch 256 (ncu --set full, profiles/r01d_summary.md)
-RUN_TRAFFIC = None
+# dram__bytes_read.sum + dram__bytes_write.sum of the persistent 66-layer run at batch 256 (ncu --set full of one launch, profiles/r01d_summary.md)
+RUN_TRAFFIC = 305.98e6 + 1145.59e6
 UNIT = "faces/s"
 
 

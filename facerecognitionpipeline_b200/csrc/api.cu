@@ -355,9 +355,9 @@ int launch_gemm2_multi_t(frb_ctx* ctx, const Gemm2Layer* d_layers, int n, int* d
     cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, d_layers, n, d_bar);
   };
-  // A cooperative launch is never combined with programmatic stream serialization here: the run's first layer must
-  // see the previous kernel's output, and the two attributes together produced wrong first-layer inputs at batch 1024
-  // (griddepcontrol.wait did not hold the cooperative grid back).  One plain stream dependency per embed costs nothing.
+  // The cooperative launch is not combined with programmatic stream serialization (FRB_MULTI_COOP_PDL=1 does, for
+  // experiments): how griddepcontrol.wait interacts with gang scheduling is not documented, and one plain stream
+  // dependency per embed costs nothing measurable.
   const bool pdl = ctx->use_pdl && (!ctx->multi_coop || getenv("FRB_MULTI_COOP_PDL") != nullptr);
   cudaError_t e = launch(pdl);
   CK(e);
