@@ -360,6 +360,15 @@ int launch_gemm2_multi_t(frb_ctx* ctx, const Gemm2Layer* d_layers, int n, int* d
   // dependency per embed costs nothing measurable.
   const bool pdl = ctx->use_pdl && (!ctx->multi_coop || getenv("FRB_MULTI_COOP_PDL") != nullptr);
   cudaError_t e = launch(pdl);
+  if (e != cudaSuccess && ctx->multi_coop) {
+    // the driver refused the cooperative attribute (e.g. a partitioned or shared device where the grid cannot be
+    // gang-scheduled): say so once and go on without the guarantee - correct whenever the GPU is not shared
+    fprintf(stderr, "frb: cooperative launch of the persistent conv run refused (%s); launching it without the attribute\n",
+            cudaGetErrorString(e));
+    cudaGetLastError();
+    ctx->multi_coop = 0;
+    e = launch(ctx->use_pdl != 0);
+  }
   CK(e);
   ctx->launches++;
   return 0;
