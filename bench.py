@@ -130,6 +130,11 @@ class CpuReference:
         from oracle import backbone, embedder
         self.threads = threads or os.cpu_count()
         torch.set_num_threads(self.threads)
+        try:   # torchrun exports OMP_NUM_THREADS=1: give numpy's BLAS (the matching half) all host threads back
+            import threadpoolctl
+            self._blas_limit = threadpoolctl.threadpool_limits(limits=self.threads)
+        except Exception:
+            self._blas_limit = None
         self.rng = np.random.default_rng(seed)
         sd = backbone.random_state_dict("ir_101", "adaface", seed, calibrate=False)
         self.emb = embedder.OracleEmbedder("ir_101", "adaface", state_dict=sd)
