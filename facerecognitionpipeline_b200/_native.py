@@ -83,6 +83,7 @@ SIGNATURES = {
     "frb_match": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "frb_match_last_flagged": (_i, [_vp]),
     "frb_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "frb_prefetch_host": (_i, [_vp, _vp, _i, _i]),
     "frb_embed_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "frb_match_host": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     "frb_embed_match_host": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),

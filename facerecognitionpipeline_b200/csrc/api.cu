@@ -127,6 +127,15 @@ struct frb_ctx {
 
   // host-API staging
   uint8_t* d_stage_u8 = nullptr; size_t stage_u8_bytes = 0;
+  // frb_prefetch_host: crops of LATER calls travel to these buffers on copy_stream while the current call computes
+  struct PrefetchSlot {
+    uint8_t* d_buf = nullptr; size_t cap = 0;
+    const uint8_t* h_ptr = nullptr; size_t bytes = 0;   // h_ptr != nullptr: an unconsumed prefetch
+    cudaEvent_t done = nullptr;
+    unsigned long long seq = 0;
+  } prefetch[2];
+  unsigned long long prefetch_seq = 0;
+  cudaStream_t copy_stream = nullptr;
   __nv_bfloat16* d_stage_in = nullptr; size_t stage_in_elems = 0;
   float* d_stage_emb = nullptr; float* d_stage_norm = nullptr; size_t stage_emb_rows = 0;
   float* d_stage_sc = nullptr; long long* d_stage_idx = nullptr; unsigned char* d_stage_acc = nullptr;
@@ -676,7 +685,7 @@ extern "C" void frb_ctx_destroy(frb_ctx* ctx) {
   cudaDeviceSynchronize();
   void* ptrs[] = {ctx->d_lut, ctx->d_wtab, ctx->d_blob, ctx->d_fc_partial, ctx->d_emb2, ctx->d_gal, ctx->d_gal_bf16,
                   ctx->d_gal_maxnorm, ctx->d_probe_f32, ctx->d_probe_bf16, ctx->d_cand_score, ctx->d_cand_idx,
-                  ctx->d_flagged, ctx->d_flag_rows, ctx->d_exact, ctx->d_scores64_tmp, ctx->d_stage_u8,
+                  ctx->d_flagged, ctx->d_flag_rows, ctx->d_exact, ctx->d_scores64_tmp, ctx->d_stage_u8, ctx->prefetch[0].d_buf, ctx->prefetch[1].d_buf,
                   ctx->d_stage_in, ctx->d_stage_emb, ctx->d_stage_norm, ctx->d_stage_sc, ctx->d_stage_idx,
                   ctx->d_stage_acc, ctx->d_jobs, ctx->d_progress, ctx->d_seg, ctx->d_sample_identity, ctx->d_id_top_idx,
                   ctx->d_id_top_sc, ctx->d_id_acc, ctx->d_id_sc32, ctx->d_id_scores, ctx->d_tail_partial, ctx->d_tail_flags, ctx->d_runs, ctx->d_run_bar};
@@ -685,6 +694,8 @@ extern "C" void frb_ctx_destroy(frb_ctx* ctx) {
   for (auto* b : ctx->d_bufs)
     if (b) cudaFree(b);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& sl : ctx->prefetch) if (sl.done) cudaEventDestroy(sl.done);
   delete ctx;
 }
 
@@ -1564,18 +1575,58 @@ int stage_match(frb_ctx* ctx, int P, int k) {
 int embed_host_locked(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S, int flags, cudaStream_t st) {
   if (S != 112 && S != 224) return fail(ctx, "S must be 112 or 224 (got %d)", S);
   const size_t in_bytes = static_cast<size_t>(B) * S * S * 3;
-  if (ensure(ctx, &ctx->d_stage_u8, &ctx->stage_u8_bytes, in_bytes)) return 1;
   if (stage_embed(ctx, B, flags)) return 1;
-  CK(cudaMemcpyAsync(ctx->d_stage_u8, h_rgb, in_bytes, cudaMemcpyHostToDevice, st));
+  const uint8_t* d_u8 = nullptr;
+  for (auto& sl : ctx->prefetch)
+    if (sl.h_ptr != nullptr && sl.h_ptr == h_rgb && sl.bytes == in_bytes) {
+      // these crops are already on their way (frb_prefetch_host): read them where they land, ordered after the copy
+      CK(cudaStreamWaitEvent(st, sl.done, 0));
+      d_u8 = sl.d_buf;
+      sl.h_ptr = nullptr;   // consumed (this call synchronises before it returns, so the slot is free afterwards)
+      break;
+    }
+  if (d_u8 == nullptr) {
+    if (ensure(ctx, &ctx->d_stage_u8, &ctx->stage_u8_bytes, in_bytes)) return 1;
+    CK(cudaMemcpyAsync(ctx->d_stage_u8, h_rgb, in_bytes, cudaMemcpyHostToDevice, st));
+    d_u8 = ctx->d_stage_u8;
+  }
   const size_t total = static_cast<size_t>(B) * 112 * 112;
   preprocess_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-      ctx->d_stage_u8, B, S, ctx->d_lut, ctx->d_stage_in, (flags & FRB_EMBED_FLIP) ? 1 : 0);
+      d_u8, B, S, ctx->d_lut, ctx->d_stage_in, (flags & FRB_EMBED_FLIP) ? 1 : 0);
   CK(cudaGetLastError());
   ctx->launches++;
   return embed_locked(ctx, ctx->d_stage_in, B, flags, ctx->d_stage_emb, ctx->d_stage_norm, nullptr, st);
 }
 
 }  // namespace
+
+// Start the host->device copy of the crops a LATER frb_embed_host / frb_embed_match_host call will be given, on a
+// separate stream, so it overlaps the call that runs in between.
+extern "C" int frb_prefetch_host(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S) {
+  if (!ctx) return 1;
+  if (B <= 0 || !h_rgb) return 0;
+  if (S != 112 && S != 224) return fail(ctx, "S must be 112 or 224 (got %d)", S);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  const size_t in_bytes = static_cast<size_t>(B) * S * S * 3;
+  // two slots: one may hold the batch the NEXT call consumes while this prefetch is for the call after it.
+  // A free slot first, else the older unconsumed one is overwritten (its copy is ordered on the copy stream).
+  frb_ctx::PrefetchSlot* sl = nullptr;
+  for (auto& c : ctx->prefetch)
+    if (c.h_ptr == h_rgb && c.bytes == in_bytes) return 0;   // already on its way
+  for (auto& c : ctx->prefetch)
+    if (c.h_ptr == nullptr) { sl = &c; break; }
+  if (!sl) sl = ctx->prefetch[0].seq < ctx->prefetch[1].seq ? &ctx->prefetch[0] : &ctx->prefetch[1];
+  if (!sl->done) CK(cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
+  if (ensure(ctx, &sl->d_buf, &sl->cap, in_bytes)) return 1;
+  CK(cudaMemcpyAsync(sl->d_buf, h_rgb, in_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CK(cudaEventRecord(sl->done, ctx->copy_stream));
+  sl->h_ptr = h_rgb;
+  sl->bytes = in_bytes;
+  sl->seq = ++ctx->prefetch_seq;
+  return 0;
+}
 
 extern "C" int frb_embed_host(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S, int flags, float* h_emb, float* h_norm) {
   if (!ctx) return 1;

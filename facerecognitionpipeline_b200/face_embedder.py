@@ -143,9 +143,11 @@ class FaceEmbedder:
         n = len(stack)
         out = np.empty((n, 512), np.float32)
         flags = self._flags | (_native.FRB_EMBED_RENORM if normalize else 0)
-        for i in range(0, n, self.max_batch):
-            chunk = np.ascontiguousarray(stack[i:i + self.max_batch])
-            dst = out[i:i + len(chunk)]
+        chunks = [np.ascontiguousarray(stack[i:i + self.max_batch]) for i in range(0, n, self.max_batch)]
+        for j, chunk in enumerate(chunks):
+            if j + 1 < len(chunks):   # the next chunk's crops travel while this one computes
+                self._ctx.frb_prefetch_host(chunks[j + 1].ctypes.data, len(chunks[j + 1]), S)
+            dst = out[j * self.max_batch:j * self.max_batch + len(chunk)]
             self._ctx.frb_embed_host(chunk.ctypes.data, len(chunk), S, flags, dst.ctypes.data, None)
         return out
 

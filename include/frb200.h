@@ -160,6 +160,11 @@ int frb_embed_host(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S, int flags, 
 /* h_probes [P][512] f32 -> h_scores [P][k], h_idx [P][k], h_accept [P] */
 int frb_match_host(frb_ctx* ctx, const float* h_probes, int P, int k, float thr, int normalize,
                    float* h_scores, long long* h_idx, unsigned char* h_accept);
+/* Streams of batches: start copying the crops of a LATER frb_embed_host / frb_embed_match_host call now (separate copy
+ * stream), so the transfer overlaps the call issued in between.  The later call recognises the same h_rgb / B / S and
+ * skips its own copy; the buffer must stay unchanged until then.  Two prefetches may be outstanding (the batch the next
+ * call takes and the one after it); a third overwrites the older. */
+int frb_prefetch_host(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S);
 /* whole path: aligned crops -> embed -> match against the uploaded gallery */
 int frb_embed_match_host(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S, int flags, int k, float thr,
                          float* h_emb, float* h_scores, long long* h_idx, unsigned char* h_accept);
