@@ -321,7 +321,8 @@ def run_ours(args):
     KNAMES = {0: "stem_tc_kernel", 1: "gemm2_sm100_kernel<64>", 2: "gemm2_sm100_kernel<128>", 3: "gemm2_sm100_kernel<256>",
               4: "conv_slab_sm100_kernel<64,1>", 5: "conv_slab_sm100_kernel<128,1>", 6: "conv_slab_sm100_kernel<128,2>",
               7: "gemm_sm100_kernel<256,0,1> + fc_finalize_kernel",
-              8: "gemm2_multi_sm100_kernel<256> (persistent run of consecutive conv layers, one launch)"}
+              8: "gemm2_multi_sm100_kernel<256> (persistent run of consecutive conv layers, one launch)",
+              9: "conv_slab_multi_sm100_kernel (persistent run of identical slab conv layers, one launch)"}
     MAXL = 256
     ms = (C.c_float * MAXL)(); kid = (C.c_int * MAXL)(); fl = (C.c_double * MAXL)(); nl = C.c_int(0)
     per_kernel = {}

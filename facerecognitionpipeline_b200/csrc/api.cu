@@ -18,6 +18,7 @@
 #include "gemm2_sm100.cuh"
 #include "gemm2_multi_sm100.cuh"
 #include "conv_slab_sm100.cuh"
+#include "conv_slab_multi_sm100.cuh"
 #include "match_sm100.cuh"
 #include "stem_sm100.cuh"
 #include "simple_kernels.cuh"
@@ -41,6 +42,8 @@ struct Plan {  // per-batch-size launch plan of the backbone
   int num_runs = 0;
   size_t run_layers = 0;           // layers in all runs = grid-barrier counters (zeroed at the start of every embed)
   std::vector<size_t> run_off;     // offset of the run's first Gemm2Layer in ctx->d_runs
+  std::vector<int> srun_len;       // same for runs of identical slab layers (conv_slab_multi_sm100_kernel)
+  std::vector<size_t> srun_off;    // offset of the run's first SlabLayer in ctx->d_sruns
   std::vector<int> use_slab;       // 1 = conv_slab_sm100_kernel (3x3 stride-1, W in {28,56,112})
   std::vector<SlabParams> sp;
   std::vector<int> slab_smem;
@@ -62,10 +65,15 @@ struct frb_ctx {
   int tail_split = 0;  // FRB_TAIL_SPLIT=1: split-K for the last partial round of the pair conv kernel (see TileItem)
   float* d_tail_partial = nullptr; size_t tail_partial_cap = 0;
   int* d_tail_flags = nullptr; size_t tail_flags_cap = 0;
+  int slab_multi = 0;  // FRB_SLAB_MULTI=1: runs of identical slab layers as ONE persistent launch as well.  Bit-identical,
+                       // but measured 0.35 ms slower per batch-256 embed: the resident weights (147 KB per CTA) must
+                       // be swapped at every layer boundary with the tensor pipe idle, while separate launches fetch
+                       // the next layer's weights before their dependency wait, under the previous layer's tail.
   int multi_coop = 1;  // FRB_MULTI_COOP=0: no cooperative-launch attribute on the persistent run kernel
   int conv_multi = 2;  // persistent multi-layer runs of the pair conv kernel: 2 = per-image dataflow between the run's
                        // layers (default), 1 = grid barrier between them, 0 = every conv layer is a launch of its own
   Gemm2Layer* d_runs = nullptr; size_t runs_cap = 0;
+  SlabLayer* d_sruns = nullptr; size_t sruns_cap = 0;
   int* d_run_bar = nullptr; size_t run_bar_cap = 0;
   int conv_quad = 0;  // FRB_QUAD: gemm2_sm100_kernel<., 4> for Cout >= 256 (1) / >= 128 (2) layers
   int quad_clusters = 0;
@@ -390,6 +398,55 @@ int launch_gemm2_multi(frb_ctx* ctx, int block_n, const Gemm2Layer* d_layers, in
   return fail(ctx, "unsupported multi-layer conv block_n=%d", block_n);
 }
 
+// One persistent launch for a run of identical slab conv layers (conv_slab_multi_sm100.cuh).
+template <int BN, int CH>
+int launch_slab_multi_t(frb_ctx* ctx, const SlabLayer* d_layers, int n, int smem_bytes, int grid, cudaStream_t st) {
+  auto kern = conv_slab_multi_sm100_kernel<BN, CH>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemm2Threads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute base[2], attr[3];
+  fill_launch_attrs(base, 2);
+  auto launch = [&](bool pdl) {
+    int na = 0;
+    attr[na++] = base[0];
+    if (pdl) attr[na++] = base[1];
+    if (ctx->multi_coop) {
+      attr[na].id = cudaLaunchAttributeCooperative;
+      attr[na].val.cooperative = 1;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kern, d_layers, n);
+  };
+  cudaError_t e = launch(ctx->use_pdl && !ctx->multi_coop);
+  if (e != cudaSuccess && ctx->multi_coop) {
+    fprintf(stderr, "frb: cooperative launch of the persistent slab run refused (%s); launching it without the attribute\n",
+            cudaGetErrorString(e));
+    cudaGetLastError();
+    ctx->multi_coop = 0;
+    e = launch(ctx->use_pdl != 0);
+  }
+  CK(e);
+  ctx->launches++;
+  return 0;
+}
+
+int launch_slab_multi(frb_ctx* ctx, int chunks, int N, const SlabLayer* d_layers, int n, int smem_bytes, int grid, cudaStream_t st) {
+  if (chunks == 1 && N == 64) return launch_slab_multi_t<64, 1>(ctx, d_layers, n, smem_bytes, grid, st);
+  if (chunks == 1 && N == 128) return launch_slab_multi_t<128, 1>(ctx, d_layers, n, smem_bytes, grid, st);
+  if (chunks == 2 && N == 128) return launch_slab_multi_t<128, 2>(ctx, d_layers, n, smem_bytes, grid, st);
+  return fail(ctx, "slab run: unsupported Cin chunks %d / Cout %d", chunks, N);
+}
+
 // NHWC bf16 activation [N][H][W][C] as a tiled 4-D tensor; box = 64 channels x box_w x box_h x 1 image.
 int make_tmap_4d_tiled(frb_ctx* ctx, CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int box_w, int box_h) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -618,6 +675,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_QUAD")) ctx->conv_quad = atoi(e);
   if (const char* e = getenv("FRB_MULTI")) ctx->conv_multi = atoi(e);
   if (const char* e = getenv("FRB_MULTI_COOP")) ctx->multi_coop = atoi(e);
+  if (const char* e = getenv("FRB_SLAB_MULTI")) ctx->slab_multi = atoi(e);
   if (const char* e = getenv("FRB_TAIL_SPLIT")) ctx->tail_split = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
   if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
@@ -688,7 +746,7 @@ extern "C" void frb_ctx_destroy(frb_ctx* ctx) {
                   ctx->d_flagged, ctx->d_flag_rows, ctx->d_exact, ctx->d_scores64_tmp, ctx->d_stage_u8, ctx->prefetch[0].d_buf, ctx->prefetch[1].d_buf,
                   ctx->d_stage_in, ctx->d_stage_emb, ctx->d_stage_norm, ctx->d_stage_sc, ctx->d_stage_idx,
                   ctx->d_stage_acc, ctx->d_jobs, ctx->d_progress, ctx->d_seg, ctx->d_sample_identity, ctx->d_id_top_idx,
-                  ctx->d_id_top_sc, ctx->d_id_acc, ctx->d_id_sc32, ctx->d_id_scores, ctx->d_tail_partial, ctx->d_tail_flags, ctx->d_runs, ctx->d_run_bar};
+                  ctx->d_id_top_sc, ctx->d_id_acc, ctx->d_id_sc32, ctx->d_id_scores, ctx->d_tail_partial, ctx->d_tail_flags, ctx->d_runs, ctx->d_run_bar, ctx->d_sruns};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto* b : ctx->d_bufs)
@@ -960,6 +1018,45 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
       CK(cudaMemcpy(ctx->d_runs, host.data(), host.size() * sizeof(Gemm2Layer), cudaMemcpyHostToDevice));
     }
   }
+  // persistent runs of identical slab layers with resident weights (stage 2 of IR-101: 24 layers; stage 1: 4)
+  pl.srun_len.assign(nl, 0); pl.srun_off.assign(nl, 0);
+  if (ctx->conv_multi >= 2 && ctx->conv_mode == 2 && !ctx->use_dataflow && ctx->slab_multi) {
+    auto same = [&](size_t a, size_t b) {
+      const frb_layer_desc &A = ctx->layers[a], &Bq = ctx->layers[b];
+      return A.cin == Bq.cin && A.cout == Bq.cout && A.hin == Bq.hin && A.win == Bq.win && pl.sp[a].nbuf == pl.sp[b].nbuf &&
+             pl.sp[a].slab_bytes == pl.sp[b].slab_bytes && pl.slab_smem[a] == pl.slab_smem[b] && pl.grid[a] == pl.grid[b];
+    };
+    auto eligible = [&](size_t i) {
+      return ctx->layers[i].op == FRB_OP_CONV && pl.use_slab[i] && pl.sp[i].b_stages == 9 * (ctx->layers[i].cin / 64) &&
+             pl.sp[i].debug == 0 && pl.sp[i].trace == nullptr && pl.grid[i] <= ctx->num_sms;
+    };
+    std::vector<SlabLayer> host;
+    size_t i = 0;
+    while (i < nl) {
+      if (!eligible(i)) { ++i; continue; }
+      size_t j = i + 1;
+      while (j < nl && eligible(j) && same(i, j)) ++j;
+      if (j - i >= 2) {
+        pl.srun_len[i] = static_cast<int>(j - i);
+        pl.srun_off[i] = host.size();
+        long long units = 0;
+        for (size_t q = i; q < j; ++q) {
+          SlabLayer sl;
+          sl.tmX = pl.tmA[q]; sl.tmB = pl.tmB[q]; sl.p = pl.sp[q];
+          sl.p.progress = ctx->d_progress;
+          sl.p.wait_target = static_cast<int>(units);
+          sl.p.sig_fence = 1;
+          units += static_cast<long long>(sl.p.H) * sl.p.W * (sl.p.N / 32);
+          host.push_back(sl);
+        }
+      }
+      i = j;
+    }
+    if (!host.empty()) {
+      if (ensure(ctx, &ctx->d_sruns, &ctx->sruns_cap, host.size())) return 1;
+      CK(cudaMemcpy(ctx->d_sruns, host.data(), host.size() * sizeof(SlabLayer), cudaMemcpyHostToDevice));
+    }
+  }
   pl.tail_flags = total_flags;
   if (total_flags > 0) {
     if (ensure(ctx, &ctx->d_tail_partial, &ctx->tail_partial_cap, max_partial)) return 1;
@@ -1003,6 +1100,13 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
     const uint8_t* blob = ctx->d_blob;
     if (ctx->profiling && i > 0) CK(cudaEventRecord(ctx->prof_events[i], st));
     if (i < run_end) continue;
+    if (pl.srun_len[i] > 1) {
+      CK(cudaMemsetAsync(ctx->d_progress, 0, sizeof(int) * Bn, st));  // run-local progress
+      if (launch_slab_multi(ctx, L.cin / 64, L.cout, ctx->d_sruns + pl.srun_off[i], pl.srun_len[i], pl.slab_smem[i], pl.grid[i], st))
+        return 1;
+      run_end = i + pl.srun_len[i];
+      continue;
+    }
     if (pl.run_len[i] > 1) {
       if (ctx->conv_multi >= 2) CK(cudaMemsetAsync(ctx->d_progress, 0, sizeof(int) * Bn, st));  // run-local progress
       if (launch_gemm2_multi(ctx, pl.block_n[i], ctx->d_runs + pl.run_off[i], pl.run_len[i], ctx->d_run_bar + pl.run_off[i],
@@ -1110,6 +1214,11 @@ extern "C" int frb_embed_profile(frb_ctx* ctx, const void* d_in, int B, int flag
     for (int q = i; q >= 0; --q)
       if (ctx->plan.run_len[q] > 1) {
         if (q + ctx->plan.run_len[q] > i) id = (q == i) ? 8 : -8;   // -8: continuation, not a launch of its own
+        break;
+      }
+    for (int q = i; q >= 0; --q)
+      if (ctx->plan.srun_len[q] > 1) {
+        if (q + ctx->plan.srun_len[q] > i) id = (q == i) ? 9 : -9;   // persistent slab run
         break;
       }
     if (h_kernel_id) h_kernel_id[i] = id;
