@@ -1246,7 +1246,7 @@ extern "C" int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, lon
   std::lock_guard<std::mutex> lk(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   CK(cudaDeviceSynchronize());
-  if (N > ctx->gal_cap) {
+  if (N > ctx->gal_cap || (ctx->gal_cap > (1ll << 20) && N < ctx->gal_cap / 8)) {   // grow, or give a much larger old gallery back
     if (ctx->d_gal) CK(cudaFree(ctx->d_gal));
     if (ctx->d_gal_bf16) CK(cudaFree(ctx->d_gal_bf16));
     ctx->d_gal = nullptr;

@@ -197,3 +197,56 @@ def test_full_size_1m_gallery_4096_probes_properties(ctx):
     eidx, esc = og.search_batch(Gh, ph, k, normalize=False)
     assert np.array_equal(ix[sub].cpu().numpy(), eidx)
     assert np.abs(s32[sub].cpu().numpy() - esc).max() <= SCORE_TOL
+
+
+def test_config5_10m_identity_gallery_sharded_equals_unsharded(ctx):
+    """BASELINE config 5 gallery size (10M identities x 512) on one GPU: the gallery is generated on the device, matched
+    whole, then as two identity shards with global ids merged by frb_topk_merge (what the NCCL path does after its
+    all-gather): ids and accept flags must be identical, planted rows come back at rank 1 with their exact f64 score."""
+    import torch
+    N, P, k, thr = 10_000_000, 256, 5, 0.5
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(17)
+    G = torch.empty((N, 512), dtype=torch.float32, device=dev)
+    for s0 in range(0, N, 1 << 20):
+        blk = torch.randn((min(1 << 20, N - s0), 512), generator=g, device=dev)
+        G[s0:s0 + blk.shape[0]] = blk / blk.norm(dim=1, keepdim=True)
+    rows = torch.randint(0, N, (P,), generator=g, device=dev)
+    probes = G[rows] + 0.03 * torch.randn((P, 512), generator=g, device=dev)
+    probes[P // 2:] = torch.randn((P - P // 2, 512), generator=g, device=dev)
+    probes = (probes / probes.norm(dim=1, keepdim=True)).contiguous()
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def match(first):
+        s32 = torch.empty((P, k), dtype=torch.float32, device=dev)
+        s64 = torch.empty((P, k), dtype=torch.float64, device=dev)
+        ix = torch.empty((P, k), dtype=torch.int64, device=dev)
+        ac = torch.empty((P,), dtype=torch.uint8, device=dev)
+        ctx.frb_match(probes.data_ptr(), P, k, thr, 0, s32.data_ptr(), ix.data_ptr(), ac.data_ptr(), s64.data_ptr(), st)
+        torch.cuda.synchronize()
+        return s32, s64, ix, ac
+
+    ctx.frb_gallery_upload(G.data_ptr(), N, 0, 1)
+    assert ctx._lib.frb_gallery_size(ctx.handle) == N
+    w32, w64, wix, wac = match(0)
+    h = P // 2
+    assert torch.equal(wix[:h, 0], rows[:h])
+    planted = (G[rows[:h]].double() * probes[:h].double()).sum(1)
+    assert (w64[:h, 0] - planted).abs().max().item() <= 1e-12
+    assert wac[:h].all() and not wac[h:].any()
+    assert (w32[:, :-1] >= w32[:, 1:]).all() and (wix >= 0).all() and (wix < N).all()
+    parts = []
+    for lo, hi in ((0, N // 2), (N // 2, N)):
+        ctx.frb_gallery_upload(G[lo:hi].data_ptr(), hi - lo, lo, 1)
+        parts.append(match(lo))
+    A = torch.stack([p[1] for p in parts]).contiguous()
+    I = torch.stack([p[2] for p in parts]).contiguous()
+    o32 = torch.empty((P, k), dtype=torch.float32, device=dev)
+    oix = torch.empty((P, k), dtype=torch.int64, device=dev)
+    oac = torch.empty((P,), dtype=torch.uint8, device=dev)
+    ctx.frb_topk_merge(A.data_ptr(), I.data_ptr(), 2, P, k, thr, o32.data_ptr(), oix.data_ptr(), oac.data_ptr(), None, st)
+    torch.cuda.synchronize()
+    assert torch.equal(oix, wix) and torch.equal(oac, wac) and torch.equal(o32, w32)
+    ctx.frb_gallery_upload(G[:256].data_ptr(), 256, 0, 1)      # release the 10M-row copies held by the context
+    del G
+    torch.cuda.empty_cache()

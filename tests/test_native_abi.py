@@ -31,6 +31,7 @@ def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(_native.WarpJob) == 8 + 16 + 48
     assert C.sizeof(_native.LayerDesc) == 23 * 4 + 4 + 4 * 8  # 23 int32 + pad + 4 int64
+    assert C.sizeof(_native.TrackResult) == 56                # frb_track_result: i64, 2 x f64, 2 x i32, i64, f64, 2 x i32
 
 
 def test_no_fallback_without_gpu():
