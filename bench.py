@@ -157,6 +157,21 @@ class CpuReference:
         t_match = (time.perf_counter() - t0) / n_probes
         return t_embed, t_match
 
+    def sample_as_is(self, n_probes=2):
+        """GalleryManager.search exactly as the reference runs it (gallery_manager.py:177-205): EVERY call rebuilds the
+        matrix with np.vstack over the students' templates before the dot product and the full argsort.  Seconds per
+        probe; a few probes only (SURVEY §8d 'as-is')."""
+        students = {i: self.G[i] for i in range(len(self.G))}      # sid -> template_embedding, dict insertion order
+        q = self.G[0]
+        t0 = time.perf_counter()
+        for _ in range(n_probes):
+            ids = list(students.keys())
+            E = np.vstack([students[sid] for sid in ids])
+            qq = q / (np.linalg.norm(q) + 1e-8)
+            s = np.dot(E, qq)
+            _ = np.argsort(s)[::-1][:5]
+        return (time.perf_counter() - t0) / n_probes
+
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the
@@ -360,9 +375,12 @@ def run_ours(args):
         ref = CpuReference(N)
         te, tm = ref.sample(64, 8)
         threads = ref.threads
-        cpu = dict(value=1.0 / (te + tm), unit=UNIT, cores=threads, kind="port",
+        t_asis = ref.sample_as_is(2)
+        cpu = dict(value=1.0 / (te + tm), unit=UNIT, cores=threads, kind="port", as_is_match_s_per_probe=t_asis,
+                   as_is_value=1.0 / (te + t_asis),
                    sample=f"64 faces torch-eager fp32 IR-101 (batch 32, {te * 1e3:.1f} ms/face) + 8 probes numpy "
-                          f"dot+argsort vs {N} x 512 f32 with the matrix cached ({tm * 1e3:.1f} ms/probe)")
+                          f"dot+argsort vs {N} x 512 f32 with the matrix cached ({tm * 1e3:.1f} ms/probe); 'as_is' = the "
+                          f"reference's search() verbatim, which re-stacks the {N} templates on every call ({t_asis:.2f} s/probe, 2 probes)")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload=f"AdaFace IR-101 batch-{B}/GPU embed + L2-norm + top-5 match vs {N}-identity "
