@@ -50,6 +50,19 @@ __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t bar_
       : "memory");
 }
 
+// same with an explicit L2 eviction-priority descriptor (CUTLASS TMA::CacheHintSm90 values)
+constexpr uint64_t kTmaEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kTmaEvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma2_load_4d_hint(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
+                                                  int c2, int c3, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "l"(hint)
+      : "memory");
+}
+
 __device__ __forceinline__ long long gtimer() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -168,6 +181,9 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           int hh = h0 - 1;
           hh = hh < 0 ? 0 : (hh > p.H - p.R - 2 ? p.H - p.R - 2 : hh);
           tma2_load_4d(&tmX, slab_full_leader0 + 8 * nbuf_i, smem_slab + nbuf_i * p.slab_bytes, u_cc * kBlockK, 0, hh, img);
+        } else if (p.debug & 512) {  // experiment: the input is dead after this layer (bar one residual read): evict it first
+          tma2_load_4d_hint(&tmX, slab_full_leader0 + 8 * nbuf_i, smem_slab + nbuf_i * p.slab_bytes, u_cc * kBlockK, -1, h0 - 1, img,
+                            kTmaEvictFirst);
         } else {
           tma2_load_4d(&tmX, slab_full_leader0 + 8 * nbuf_i, smem_slab + nbuf_i * p.slab_bytes, u_cc * kBlockK, -1, h0 - 1, img);
         }
