@@ -791,16 +791,16 @@ extern "C" int frb_warp_normalize(frb_ctx* ctx, const void* d_src_base, const fr
     ctx->jobs_cap = B;
   }
   CK(cudaMemcpyAsync(ctx->d_jobs, h_jobs, sizeof(WarpJob) * B, cudaMemcpyHostToDevice, st));
-  dim3 grid((S * S + 127) / 128, B);
+  dim3 grid((S * S + kWarpPixPerBlock - 1) / kWarpPixPerBlock, B);
   const uint8_t* src = reinterpret_cast<const uint8_t*>(d_src_base);
   uint8_t* o8 = reinterpret_cast<uint8_t*>(d_out_u8);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(d_out_bf16);
   if (d_out_u8 && d_out_bf16)
-    warp_normalize_kernel<true, true><<<grid, 128, 0, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+    warp_normalize_kernel<true, true><<<grid, kWarpThreads, 0, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
   else if (d_out_u8)
-    warp_normalize_kernel<true, false><<<grid, 128, 0, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+    warp_normalize_kernel<true, false><<<grid, kWarpThreads, 0, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
   else
-    warp_normalize_kernel<false, true><<<grid, 128, 0, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+    warp_normalize_kernel<false, true><<<grid, kWarpThreads, 0, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
   CK(cudaGetLastError());
   ctx->launches++;
   return 0;

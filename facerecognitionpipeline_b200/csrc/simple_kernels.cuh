@@ -34,26 +34,58 @@ __device__ __forceinline__ int cv_round_sat(double v) {
 
 // wtab: [32*32][4] uint16 bilinear weights (sum exactly 32768), built on the host the way
 // cv::initInterTab2D builds BilinearTab_i.  lut: 256 bf16 bit patterns of the normalised value.
+// One thread per output pixel (adjacent lanes read adjacent source pixels: the best coalescing this gather allows).
+// The inverse matrix is a per-face constant: one thread per block computes it in the exact operation order of
+// cv::invertAffineTransform and shares it through shared memory.  The 2x2 tap block is fetched as two 6-byte runs
+// (pixels sx, sx+1 of rows sy, sy+1) with aligned 32-bit loads + funnel shifts instead of twelve byte loads, which
+// halves the L1 tag traffic that bounds this kernel; taps that touch the border take the byte path (zero fill).
+__device__ __forceinline__ void warp_load6(const uint8_t* p, uint32_t* lo, uint32_t* hi) {
+  // bytes p[0..5] -> lo = p[0..3], hi = p[4..5] (upper half undefined); reads only aligned words that contain them
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
+  const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+  const uint32_t w2 = (sh == 24) ? __ldg(w + 2) : 0u;
+  *lo = __funnelshift_r(w0, w1, sh);
+  *hi = __funnelshift_r(w1, w2, sh);
+}
+constexpr int kWarpThreads = 256, kWarpPixPerBlock = 2048;   // 8 pixels per thread, 256 apart (lanes stay adjacent)
 template <bool kWriteU8, bool kWriteBf16>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kWarpThreads)
 warp_normalize_kernel(const uint8_t* __restrict__ src_base, const WarpJob* __restrict__ jobs, int S,
-                      const unsigned short* __restrict__ wtab, const unsigned short* __restrict__ lut,
+                      const unsigned short* __restrict__ wtab_g, const unsigned short* __restrict__ lut_g,
                       uint8_t* __restrict__ out_u8, __nv_bfloat16* __restrict__ out_bf16) {
+  __shared__ double s_m[6];          // m00, m01, m10, m11, b1, b2 of the inverse map
+  __shared__ WarpJob s_job;
+  // the bilinear weight table (8 KB) and the normalisation LUT live in shared memory: every global load goes through
+  // the L1 tag stage, which is what bounds this gather
+  __shared__ __align__(8) unsigned short wtab[kInterTab * kInterTab * 4];
+  __shared__ unsigned short lut[256];
+  for (int i = threadIdx.x; i < kInterTab * kInterTab; i += kWarpThreads)
+    reinterpret_cast<uint2*>(wtab)[i] = __ldg(reinterpret_cast<const uint2*>(wtab_g) + i);
+  if (threadIdx.x < 256) lut[threadIdx.x] = lut_g[threadIdx.x];
   const int face = blockIdx.y;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= S * S) return;
-  const WarpJob jb = jobs[face];
-  // invert (double, unfused: mirrors the scalar C++ in cv::warpAffine / cv::invertAffineTransform)
-  double D = __dsub_rn(__dmul_rn(jb.M[0], jb.M[4]), __dmul_rn(jb.M[1], jb.M[3]));
-  D = (D != 0.0) ? __ddiv_rn(1.0, D) : 0.0;
-  const double A11 = __dmul_rn(jb.M[4], D), A22 = __dmul_rn(jb.M[0], D);
-  const double m00 = A11;
-  const double m01 = __dmul_rn(jb.M[1], -D);
-  const double m10 = __dmul_rn(jb.M[3], -D);
-  const double m11 = A22;
-  const double b1 = __dsub_rn(__dmul_rn(-m00, jb.M[2]), __dmul_rn(m01, jb.M[5]));
-  const double b2 = __dsub_rn(__dmul_rn(-m10, jb.M[2]), __dmul_rn(m11, jb.M[5]));
-
+  if (threadIdx.x == 0) {
+    const WarpJob jb = jobs[face];
+    s_job = jb;
+    // invert (double, unfused: mirrors the scalar C++ in cv::warpAffine / cv::invertAffineTransform)
+    double D = __dsub_rn(__dmul_rn(jb.M[0], jb.M[4]), __dmul_rn(jb.M[1], jb.M[3]));
+    D = (D != 0.0) ? __ddiv_rn(1.0, D) : 0.0;
+    const double A11 = __dmul_rn(jb.M[4], D), A22 = __dmul_rn(jb.M[0], D);
+    const double m00 = A11;
+    const double m01 = __dmul_rn(jb.M[1], -D);
+    const double m10 = __dmul_rn(jb.M[3], -D);
+    const double m11 = A22;
+    s_m[0] = m00; s_m[1] = m01; s_m[2] = m10; s_m[3] = m11;
+    s_m[4] = __dsub_rn(__dmul_rn(-m00, jb.M[2]), __dmul_rn(m01, jb.M[5]));
+    s_m[5] = __dsub_rn(__dmul_rn(-m10, jb.M[2]), __dmul_rn(m11, jb.M[5]));
+  }
+  __syncthreads();
+  const double m00 = s_m[0], m01 = s_m[1], m10 = s_m[2], m11 = s_m[3], b1 = s_m[4], b2 = s_m[5];
+  const int srcH = s_job.H, srcW = s_job.W, pitch = s_job.pitch;
+  const uint8_t* img = src_base + s_job.src_off;
+  const int pix_end = min(S * S, (static_cast<int>(blockIdx.x) + 1) * kWarpPixPerBlock);
+  for (int pix = blockIdx.x * kWarpPixPerBlock + threadIdx.x; pix < pix_end; pix += kWarpThreads) {
   const int y = pix / S, x = pix - y * S;
   const int round_delta = kAbScale / kInterTab / 2;
   const int adelta = cv_round_sat(__dmul_rn(__dmul_rn(m00, (double)x), (double)kAbScale));
@@ -67,30 +99,39 @@ warp_normalize_kernel(const uint8_t* __restrict__ src_base, const WarpJob* __res
   const ushort4 w4 = reinterpret_cast<const ushort4*>(wtab)[ay * kInterTab + ax];
   // weights are 0..32768 inclusive (the (0,0) phase is exactly 32768): keep them unsigned
   const int4 w = make_int4(w4.x, w4.y, w4.z, w4.w);
-
-  const uint8_t* img = src_base + jb.src_off;
   int acc0 = 0, acc1 = 0, acc2 = 0;
-  const bool x0ok = (sx >= 0 && sx < jb.W), x1ok = (sx + 1 >= 0 && sx + 1 < jb.W);
-  if (sy >= 0 && sy < jb.H) {
-    const uint8_t* rowp = img + static_cast<size_t>(sy) * jb.pitch;
-    if (x0ok) {
-      const uint8_t* q = rowp + 3 * sx;
-      acc0 += w.x * q[0]; acc1 += w.x * q[1]; acc2 += w.x * q[2];
+  if (sx >= 0 && sx + 3 <= srcW && sy >= 0 && sy + 1 < srcH) {
+    // interior: every byte of the aligned words lies inside the image (3 * sx + 9 <= 3 * W)
+    const uint8_t* q0 = img + static_cast<size_t>(sy) * pitch + 3 * sx;
+    uint32_t lo0, hi0, lo1, hi1;
+    warp_load6(q0, &lo0, &hi0);
+    warp_load6(q0 + pitch, &lo1, &hi1);
+    acc0 = w.x * (lo0 & 0xff) + w.y * (lo0 >> 24) + w.z * (lo1 & 0xff) + w.w * (lo1 >> 24);
+    acc1 = w.x * ((lo0 >> 8) & 0xff) + w.y * (hi0 & 0xff) + w.z * ((lo1 >> 8) & 0xff) + w.w * (hi1 & 0xff);
+    acc2 = w.x * ((lo0 >> 16) & 0xff) + w.y * ((hi0 >> 8) & 0xff) + w.z * ((lo1 >> 16) & 0xff) + w.w * ((hi1 >> 8) & 0xff);
+  } else {
+    const bool x0ok = (sx >= 0 && sx < srcW), x1ok = (sx + 1 >= 0 && sx + 1 < srcW);
+    if (sy >= 0 && sy < srcH) {
+      const uint8_t* rowp = img + static_cast<size_t>(sy) * pitch;
+      if (x0ok) {
+        const uint8_t* q = rowp + 3 * sx;
+        acc0 += w.x * q[0]; acc1 += w.x * q[1]; acc2 += w.x * q[2];
+      }
+      if (x1ok) {
+        const uint8_t* q = rowp + 3 * (sx + 1);
+        acc0 += w.y * q[0]; acc1 += w.y * q[1]; acc2 += w.y * q[2];
+      }
     }
-    if (x1ok) {
-      const uint8_t* q = rowp + 3 * (sx + 1);
-      acc0 += w.y * q[0]; acc1 += w.y * q[1]; acc2 += w.y * q[2];
-    }
-  }
-  if (sy + 1 >= 0 && sy + 1 < jb.H) {
-    const uint8_t* rowp = img + static_cast<size_t>(sy + 1) * jb.pitch;
-    if (x0ok) {
-      const uint8_t* q = rowp + 3 * sx;
-      acc0 += w.z * q[0]; acc1 += w.z * q[1]; acc2 += w.z * q[2];
-    }
-    if (x1ok) {
-      const uint8_t* q = rowp + 3 * (sx + 1);
-      acc0 += w.w * q[0]; acc1 += w.w * q[1]; acc2 += w.w * q[2];
+    if (sy + 1 >= 0 && sy + 1 < srcH) {
+      const uint8_t* rowp = img + static_cast<size_t>(sy + 1) * pitch;
+      if (x0ok) {
+        const uint8_t* q = rowp + 3 * sx;
+        acc0 += w.z * q[0]; acc1 += w.z * q[1]; acc2 += w.z * q[2];
+      }
+      if (x1ok) {
+        const uint8_t* q = rowp + 3 * (sx + 1);
+        acc0 += w.w * q[0]; acc1 += w.w * q[1]; acc2 += w.w * q[2];
+      }
     }
   }
   // FixedPtCast<int, uchar, 15>: (v + 2^14) >> 15, saturated
@@ -105,6 +146,7 @@ warp_normalize_kernel(const uint8_t* __restrict__ src_base, const WarpJob* __res
     unsigned short* ob = reinterpret_cast<unsigned short*>(out_bf16) + o;
     ob[0] = lut[b]; ob[1] = lut[g]; ob[2] = lut[r];
   }
+  }  // pixel loop
 }
 
 // ------------------------------------------------------------------ preprocess (aligned crops)
