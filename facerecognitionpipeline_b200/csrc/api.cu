@@ -149,6 +149,10 @@ struct frb_ctx {
   float* d_stage_sc = nullptr; long long* d_stage_idx = nullptr; unsigned char* d_stage_acc = nullptr;
   size_t stage_match_rows = 0; int stage_match_k = 0;
   WarpJob* d_jobs = nullptr; int jobs_cap = 0;
+  std::vector<int> h_boxes;      // per-face source boxes of the last frb_warp_normalize call
+  int warp_staged = 0;           // FRB_WARP_STAGED=1: stage each face's source box in shared memory first (bit-identical;
+                                 // measured SLOWER, 1.14 vs 0.75 ms for 8192 faces: one 200 KB block per SM serialises
+                                 // load and gather).  Default: the global-memory gather.
   cudaStream_t own_stream = nullptr;
 };
 
@@ -676,6 +680,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_MULTI")) ctx->conv_multi = atoi(e);
   if (const char* e = getenv("FRB_MULTI_COOP")) ctx->multi_coop = atoi(e);
   if (const char* e = getenv("FRB_SLAB_MULTI")) ctx->slab_multi = atoi(e);
+  if (const char* e = getenv("FRB_WARP_STAGED")) ctx->warp_staged = atoi(e);
   if (const char* e = getenv("FRB_TAIL_SPLIT")) ctx->tail_split = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
   if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
@@ -781,20 +786,71 @@ extern "C" int frb_warp_normalize(frb_ctx* ctx, const void* d_src_base, const fr
   if (B <= 0) return 0;
   if (d_out_bf16 && S != 112) return fail(ctx, "frb_warp_normalize: bf16 output requires S == 112");
   if (!d_out_u8 && !d_out_bf16) return fail(ctx, "frb_warp_normalize: no output requested");
+  if (S < 64 || S > kWarpMaxS) return fail(ctx, "frb_warp_normalize: S must be in [64, %d] (got %d)", kWarpMaxS, S);
   std::lock_guard<std::mutex> lk(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (ctx->jobs_cap < B) {
     if (ctx->d_jobs) CK(cudaFree(ctx->d_jobs));
     ctx->d_jobs = nullptr;
-    CK(cudaMalloc(&ctx->d_jobs, sizeof(WarpJob) * B));
-    ctx->jobs_cap = B;
+    const int cap = (B + 1) & ~1;   // even: the boxes behind the 72-byte jobs stay 16-byte aligned
+    CK(cudaMalloc(&ctx->d_jobs, (sizeof(WarpJob) + sizeof(int4)) * cap));   // jobs, then one source box per face
+    ctx->jobs_cap = cap;
   }
   CK(cudaMemcpyAsync(ctx->d_jobs, h_jobs, sizeof(WarpJob) * B, cudaMemcpyHostToDevice, st));
-  dim3 grid((S * S + kWarpPixPerBlock - 1) / kWarpPixPerBlock, B);
   const uint8_t* src = reinterpret_cast<const uint8_t*>(d_src_base);
   uint8_t* o8 = reinterpret_cast<uint8_t*>(d_out_u8);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(d_out_bf16);
+  // Source box of every face (the output square's corners through the inverse map, two pixels of slack, clamped to the
+  // image).  When all of them fit in shared memory the staged kernel reads each source byte once with coalesced loads.
+  if (ctx->warp_staged) {
+    ctx->h_boxes.resize(static_cast<size_t>(B) * 4);
+    size_t max_bytes = 0;
+    const WarpJob* hj = reinterpret_cast<const WarpJob*>(h_jobs);
+    for (int i = 0; i < B; ++i) {
+      const double* M = hj[i].M;
+      double D = M[0] * M[4] - M[1] * M[3];
+      D = D != 0.0 ? 1.0 / D : 0.0;
+      const double m00 = M[4] * D, m01 = -M[1] * D, m10 = -M[3] * D, m11 = M[0] * D;
+      const double b1 = -m00 * M[2] - m01 * M[5], b2 = -m10 * M[2] - m11 * M[5];
+      double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+      for (int c = 0; c < 4; ++c) {
+        const double x = (c & 1) ? S - 1 : 0, y = (c & 2) ? S - 1 : 0;
+        const double sx = m00 * x + m01 * y + b1, sy = m10 * x + m11 * y + b2;
+        xmin = std::min(xmin, sx); xmax = std::max(xmax, sx); ymin = std::min(ymin, sy); ymax = std::max(ymax, sy);
+      }
+      int x0 = static_cast<int>(std::floor(xmin)) - 2, x1 = static_cast<int>(std::ceil(xmax)) + 3;
+      int y0 = static_cast<int>(std::floor(ymin)) - 2, y1 = static_cast<int>(std::ceil(ymax)) + 3;
+      x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, hj[i].W - 1); y1 = std::min(y1, hj[i].H - 1);
+      if (!(std::isfinite(xmin) && std::isfinite(xmax) && std::isfinite(ymin) && std::isfinite(ymax))) { x0 = y0 = 0; x1 = y1 = -1; }
+      int* bx = &ctx->h_boxes[static_cast<size_t>(i) * 4];
+      bx[0] = x0; bx[1] = y0; bx[2] = x1; bx[3] = y1;
+      if (x1 >= x0 && y1 >= y0)
+        max_bytes = std::max(max_bytes, static_cast<size_t>(y1 - y0 + 1) * warp_staged_pitch(x0, x1));
+    }
+    if (max_bytes <= static_cast<size_t>(kWarpStagedMaxBytes)) {
+      int4* d_boxes = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(ctx->d_jobs) + sizeof(WarpJob) * static_cast<size_t>(ctx->jobs_cap));
+      CK(cudaMemcpyAsync(d_boxes, ctx->h_boxes.data(), sizeof(int4) * B, cudaMemcpyHostToDevice, st));
+      static bool attr_set = false;
+      if (!attr_set) {
+        CK(cudaFuncSetAttribute(warp_normalize_staged_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpStagedMaxBytes));
+        CK(cudaFuncSetAttribute(warp_normalize_staged_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpStagedMaxBytes));
+        CK(cudaFuncSetAttribute(warp_normalize_staged_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpStagedMaxBytes));
+        attr_set = true;
+      }
+      const size_t smem = std::max<size_t>(max_bytes, 16);
+      if (d_out_u8 && d_out_bf16)
+        warp_normalize_staged_kernel<true, true><<<B, kWarpStagedThreads, smem, st>>>(src, ctx->d_jobs, d_boxes, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+      else if (d_out_u8)
+        warp_normalize_staged_kernel<true, false><<<B, kWarpStagedThreads, smem, st>>>(src, ctx->d_jobs, d_boxes, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+      else
+        warp_normalize_staged_kernel<false, true><<<B, kWarpStagedThreads, smem, st>>>(src, ctx->d_jobs, d_boxes, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+      CK(cudaGetLastError());
+      ctx->launches++;
+      return 0;
+    }
+  }
+  dim3 grid((S * S + kWarpPixPerBlock - 1) / kWarpPixPerBlock, B);
   if (d_out_u8 && d_out_bf16)
     warp_normalize_kernel<true, true><<<grid, kWarpThreads, 0, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
   else if (d_out_u8)
