@@ -150,6 +150,7 @@ struct frb_ctx {
   size_t stage_match_rows = 0; int stage_match_k = 0;
   WarpJob* d_jobs = nullptr; int jobs_cap = 0;
   std::vector<int> h_boxes;      // per-face source boxes of the last frb_warp_normalize call
+  int match_prefetch = 0;        // FRB_MATCH_PREFETCH=n: L2-prefetch gallery tiles n ahead of the TMA ring (pair kernel)
   int warp_staged = 0;           // FRB_WARP_STAGED=1: stage each face's source box in shared memory first (bit-identical;
                                  // measured SLOWER, 1.14 vs 0.75 ms for 8192 faces: one 200 KB block per SM serialises
                                  // load and gather).  Default: the global-memory gather.
@@ -681,6 +682,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_MULTI_COOP")) ctx->multi_coop = atoi(e);
   if (const char* e = getenv("FRB_SLAB_MULTI")) ctx->slab_multi = atoi(e);
   if (const char* e = getenv("FRB_WARP_STAGED")) ctx->warp_staged = atoi(e);
+  if (const char* e = getenv("FRB_MATCH_PREFETCH")) ctx->match_prefetch = atoi(e);
   if (const char* e = getenv("FRB_TAIL_SPLIT")) ctx->tail_split = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
   if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
@@ -1450,6 +1452,7 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
   MatchParams mp;
   mp.P = P;
   mp.N = N;
+  mp.prefetch_tiles = ctx->match_prefetch;
   const bool pair_mode = P > 128 && ctx->match_pair;   // two probe tiles per CTA pair (match_filter2_kernel)
   const int units = pair_mode ? ctx->num_sms / 2 : ctx->num_sms;  // concurrently running work items
   mp.p_tiles = pair_mode ? (P + 255) / 256 : (P + 127) / 128;

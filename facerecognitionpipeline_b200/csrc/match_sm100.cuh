@@ -30,7 +30,15 @@ constexpr int kMatchThreads = 192;
 constexpr int kGalGroup = 128;
 __host__ __device__ __forceinline__ int gallery_box_row(int group, int kb) { return (group * kMatchKB + kb) * kGalGroup; }
 
+// L2 prefetch of a 2-D tiled box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 struct MatchParams {
+  int prefetch_tiles;    // gallery tiles pulled into L2 ahead of the TMA ring (0 = off)
   int P;                 // probes
   long long N;           // gallery rows held by this rank
   int p_tiles;           // ceil(P / 128)
@@ -381,6 +389,10 @@ match_filter2_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * S::kBBytes);
             tma2_load_2d(&tmG2, b_full_leader0 + 8 * stage, smem_b + stage * S::kBBytes, 0, gallery_box_row(2 * t + crank, kb));
+            // the ring holds 96 KB per SM; with few probes the filter is HBM-bound, so more bytes are kept in flight by
+            // pulling the same K block of a later tile into L2 now
+            if (p.prefetch_tiles > 0 && t + p.prefetch_tiles < t_end)
+              tma_prefetch_2d(&tmG2, 0, gallery_box_row(2 * (t + p.prefetch_tiles) + crank, kb));
           }
           __syncwarp();
           if (++stage == kMatch2BStages) {
