@@ -131,3 +131,33 @@ def test_large_batch_256_ir101_config2(ctx):
     assert np.array_equal(big[100:108], small)
     ref = oe.OracleEmbedder("ir_101", "adaface", state_dict=sd).extract_embeddings_batch(crops[:8])
     assert _cos(big[:8], ref).min() >= COS_MIN
+
+
+def test_chunked_prefetch_and_threads(ir50, ctx):
+    """Chunked embedding (each chunk's crops are handed to frb_prefetch_host while the previous chunk computes) gives
+    the same bytes as one chunk; a prefetch that is never consumed is harmless; and calls from several host threads on
+    the shared context (the reference server runs Flask threaded, face_recognition_server.py:1102) serialise on the
+    context mutex and return what the sequential calls return."""
+    import threading
+    sd, fe, orc = ir50
+    crops = _crops(np.random.default_rng(41), 100)
+    fe.max_batch = 128
+    whole = fe.extract_embeddings_batch(crops)
+    fe.max_batch = 32                                    # chunks of 32, 32, 32, 4 with prefetch between them
+    chunked = fe.extract_embeddings_batch(crops)
+    assert np.array_equal(whole, chunked)
+    stray = np.ascontiguousarray(np.stack(crops[:7]))
+    ctx.frb_prefetch_host(stray.ctypes.data, 7, 112)     # never consumed
+    assert np.array_equal(fe.extract_embeddings_batch(crops[:40]), whole[:40])
+    out = [None] * 4
+
+    def work(i):
+        out[i] = fe.extract_embeddings_batch(crops[i * 25:(i + 1) * 25])
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert np.array_equal(np.concatenate(out), whole)
+    fe.max_batch = 256
