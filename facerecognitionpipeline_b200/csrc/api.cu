@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -155,9 +156,14 @@ struct frb_ctx {
                                  // measured SLOWER, 1.14 vs 0.75 ms for 8192 faces: one 200 KB block per SM serialises
                                  // load and gather).  Default: the global-memory gather.
   cudaStream_t own_stream = nullptr;
+  std::set<const void*> smem_attr_done;   // kernels whose dynamic shared-memory limit was raised on this device
 };
 
 namespace {
+
+int fail(frb_ctx* c, const char* fmt, ...);
+// dynamic shared memory opt-in: a function attribute is per device, so it is remembered per context, not per process
+int set_smem_attr(frb_ctx* ctx, const void* kernel, int bytes);
 
 int fail(frb_ctx* c, const char* fmt, ...) {
   char buf[1024];
@@ -175,6 +181,13 @@ int fail(frb_ctx* c, const char* fmt, ...) {
     if (e_ != cudaSuccess)                                                               \
       return fail(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
   } while (0)
+
+int set_smem_attr(frb_ctx* ctx, const void* kernel, int bytes) {
+  if (ctx->smem_attr_done.count(kernel)) return 0;
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  ctx->smem_attr_done.insert(kernel);
+  return 0;
+}
 
 template <typename T>
 int ensure(frb_ctx* ctx, T** p, size_t* cap, size_t need) {
@@ -242,11 +255,7 @@ template <int BN, int MODE, int CL>
 int launch_gemm_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& gp,
                   int grid, cudaStream_t st) {
   auto kern = gemm_sm100_kernel<BN, MODE, CL>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
-    attr_set = true;
-  }
+  if (set_smem_attr(ctx, reinterpret_cast<const void*>(kern), GemmSmem<BN>::kTotal)) return 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemmThreads);
@@ -286,11 +295,7 @@ template <int BN, int CL>
 int launch_gemm2_t(frb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& gp,
                    int grid, cudaStream_t st) {
   auto kern = gemm2_sm100_kernel<BN, CL>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::kTotal));
-    attr_set = true;
-  }
+  if (set_smem_attr(ctx, reinterpret_cast<const void*>(kern), Gemm2Smem<BN>::kTotal)) return 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemm2Threads);
@@ -349,11 +354,7 @@ int launch_conv(frb_ctx* ctx, int block_n, const CUtensorMap& a, const CUtensorM
 template <int BN>
 int launch_gemm2_multi_t(frb_ctx* ctx, const Gemm2Layer* d_layers, int n, int* d_bar, int grid, cudaStream_t st) {
   auto kern = gemm2_multi_sm100_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::kTotal));
-    attr_set = true;
-  }
+  if (set_smem_attr(ctx, reinterpret_cast<const void*>(kern), Gemm2Smem<BN>::kTotal)) return 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemm2Threads);
@@ -407,11 +408,7 @@ int launch_gemm2_multi(frb_ctx* ctx, int block_n, const Gemm2Layer* d_layers, in
 template <int BN, int CH>
 int launch_slab_multi_t(frb_ctx* ctx, const SlabLayer* d_layers, int n, int smem_bytes, int grid, cudaStream_t st) {
   auto kern = conv_slab_multi_sm100_kernel<BN, CH>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  if (set_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024)) return 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemm2Threads);
@@ -525,11 +522,7 @@ template <int BN, int CH>
 int launch_slab_t(frb_ctx* ctx, const CUtensorMap& x, const CUtensorMap& b, const SlabParams& sp, int smem_bytes, int grid,
                   cudaStream_t st) {
   auto kern = conv_slab_sm100_kernel<BN, CH>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  if (set_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024)) return 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemm2Threads);
@@ -833,13 +826,9 @@ extern "C" int frb_warp_normalize(frb_ctx* ctx, const void* d_src_base, const fr
     if (max_bytes <= static_cast<size_t>(kWarpStagedMaxBytes)) {
       int4* d_boxes = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(ctx->d_jobs) + sizeof(WarpJob) * static_cast<size_t>(ctx->jobs_cap));
       CK(cudaMemcpyAsync(d_boxes, ctx->h_boxes.data(), sizeof(int4) * B, cudaMemcpyHostToDevice, st));
-      static bool attr_set = false;
-      if (!attr_set) {
-        CK(cudaFuncSetAttribute(warp_normalize_staged_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpStagedMaxBytes));
-        CK(cudaFuncSetAttribute(warp_normalize_staged_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpStagedMaxBytes));
-        CK(cudaFuncSetAttribute(warp_normalize_staged_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpStagedMaxBytes));
-        attr_set = true;
-      }
+      if (set_smem_attr(ctx, reinterpret_cast<const void*>(warp_normalize_staged_kernel<true, true>), kWarpStagedMaxBytes)) return 1;
+      if (set_smem_attr(ctx, reinterpret_cast<const void*>(warp_normalize_staged_kernel<true, false>), kWarpStagedMaxBytes)) return 1;
+      if (set_smem_attr(ctx, reinterpret_cast<const void*>(warp_normalize_staged_kernel<false, true>), kWarpStagedMaxBytes)) return 1;
       const size_t smem = std::max<size_t>(max_bytes, 16);
       if (d_out_u8 && d_out_bf16)
         warp_normalize_staged_kernel<true, true><<<B, kWarpStagedThreads, smem, st>>>(src, ctx->d_jobs, d_boxes, S, ctx->d_wtab, ctx->d_lut, o8, ob);
@@ -1175,11 +1164,7 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
     }
     if (L.op == FRB_OP_STEM) {
       const void* in = L.in_buf < 0 ? d_in : ctx->d_bufs[L.in_buf];
-      static bool attr_set = false;
-      if (!attr_set) {
-        CK(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
-        attr_set = true;
-      }
+      if (set_smem_attr(ctx, reinterpret_cast<const void*>(stem_tc_kernel), kStemSmemBytes)) return 1;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(Bn * (L.hin / kStemRows));
       cfg.blockDim = dim3(kStemThreads);
@@ -1492,11 +1477,7 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
   CUtensorMap tmP;
   if (make_tmap_2d(ctx, &tmP, ctx->d_probe_bf16, 512, static_cast<uint64_t>(P), 128)) return 1;
   if (pair_mode) {
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      CK(cudaFuncSetAttribute(match_filter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Match2Smem::kTotal));
-      attr2_set = true;
-    }
+    if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_filter2_kernel), Match2Smem::kTotal)) return 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(std::min(mp.p_tiles * mp.slices, units) * 2);
     cfg.blockDim = dim3(kMatch2Threads);
@@ -1508,11 +1489,7 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
     cfg.numAttrs = 1;
     CK(cudaLaunchKernelEx(&cfg, match_filter2_kernel, tmP, ctx->tmG2, mp));
   } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CK(cudaFuncSetAttribute(match_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MatchSmem::kTotal));
-      attr_set = true;
-    }
+    if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_filter_kernel), MatchSmem::kTotal)) return 1;
     const int grid = std::min(mp.p_tiles * mp.slices, ctx->num_sms);
     match_filter_kernel<<<grid, kMatchThreads, MatchSmem::kTotal, st>>>(tmP, ctx->tmG, mp);
   }
@@ -1960,11 +1937,7 @@ extern "C" int frb_debug_im2col(frb_ctx* ctx, const void* d_in, int B, int H, in
   if (make_tmap_im2col(ctx, &tm, d_in, B, H, W, C, ksize, stride, pad)) return 1;
   const int P = out_dim(H, ksize, stride, pad), Q = out_dim(W, ksize, stride, pad);
   const int img = m0 / (P * Q), rem = m0 % (P * Q), pp = rem / Q, qq = rem % Q;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(im2col_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 64 + 1024));
-    attr_set = true;
-  }
+  if (set_smem_attr(ctx, reinterpret_cast<const void*>(im2col_dump_kernel), 16384 + 64 + 1024)) return 1;
   im2col_dump_kernel<<<1, 128, 16384 + 64 + 1024, static_cast<cudaStream_t>(stream)>>>(
       tm, c0, qq * stride - pad, pp * stride - pad, img, tap_s, tap_r, reinterpret_cast<uint4*>(d_out_16k));
   CK(cudaGetLastError());
@@ -2044,11 +2017,7 @@ extern "C" int frb_debug_shift_mma(frb_ctx* ctx, const void* d_slab_256x64, cons
   CUtensorMap ta, tb;
   if (make_tmap_2d(ctx, &ta, d_slab_256x64, 64, 256, 128)) return 1;
   if (make_tmap_2d(ctx, &tb, d_B_64x64, 64, 64, 64)) return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(shift_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8192 + 64 + 1024));
-    attr_set = true;
-  }
+  if (set_smem_attr(ctx, reinterpret_cast<const void*>(shift_mma_kernel), 32768 + 8192 + 64 + 1024)) return 1;
   shift_mma_kernel<<<1, 128, 32768 + 8192 + 64 + 1024, static_cast<cudaStream_t>(stream)>>>(ta, tb, j0, mode, d_out_128x64);
   CK(cudaGetLastError());
   ctx->launches++;
