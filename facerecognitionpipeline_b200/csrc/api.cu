@@ -151,6 +151,7 @@ struct frb_ctx {
   size_t stage_match_rows = 0; int stage_match_k = 0;
   WarpJob* d_jobs = nullptr; int jobs_cap = 0;
   std::vector<int> h_boxes;      // per-face source boxes of the last frb_warp_normalize call
+  int slab_min_w = 0;            // FRB_SLAB_MINW=56: 28-pixel layers use the im2col pair kernel instead of the slab kernel
   int match_prefetch = 0;        // FRB_MATCH_PREFETCH=n: L2-prefetch gallery tiles n ahead of the TMA ring (pair kernel)
   int warp_staged = 0;           // FRB_WARP_STAGED=1: stage each face's source box in shared memory first (bit-identical;
                                  // measured SLOWER, 1.14 vs 0.75 ms for 8192 faces: one 200 KB block per SM serialises
@@ -468,6 +469,7 @@ int slab_rows(int w) { return w == 112 ? 1 : (w == 56 ? 2 : (w == 28 ? 4 : 0)); 
 bool slab_eligible(const frb_ctx* ctx, const frb_layer_desc& L, bool has_sc) {
   if (ctx->conv_mode != 2 || !ctx->use_slab) return false;
   if (L.ksize != 3 || L.stride != 1 || L.pad != 1 || has_sc) return false;
+  if (L.win < ctx->slab_min_w) return false;   // experiments: narrower layers go to the im2col pair kernel (and its persistent run)
   if (L.hin != L.win || slab_rows(L.win) == 0 || L.hin % slab_rows(L.win)) return false;
   // Cout = 256 (weights cannot stay resident) measured slower than the im2col pair kernel: not eligible
   if (!((L.cin == 64 && (L.cout == 64 || L.cout == 128)) || (L.cin == 128 && (L.cout == 128 || (L.cout == 256 && getenv("FRB_SLAB_N256")))))) return false;
@@ -676,6 +678,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_SLAB_MULTI")) ctx->slab_multi = atoi(e);
   if (const char* e = getenv("FRB_WARP_STAGED")) ctx->warp_staged = atoi(e);
   if (const char* e = getenv("FRB_MATCH_PREFETCH")) ctx->match_prefetch = atoi(e);
+  if (const char* e = getenv("FRB_SLAB_MINW")) ctx->slab_min_w = atoi(e);
   if (const char* e = getenv("FRB_TAIL_SPLIT")) ctx->tail_split = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
   if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
