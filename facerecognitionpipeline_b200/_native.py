@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import threading
 from pathlib import Path
 
 _PKG_DIR = Path(__file__).resolve().parent
@@ -75,14 +76,25 @@ SIGNATURES = {
     "frb_backbone_flops_per_face": (C.c_double, [_vp]),
     "frb_gallery_upload": (_i, [_vp, _vp, _ll, _ll, _i]),
     "frb_gallery_size": (_ll, [_vp]),
+    "frb_gallery_generation": (_ll, [_vp]),
+    "frb_backbone_generation": (_ll, [_vp]),
     "frb_gallery_upload_samples": (_i, [_vp, _vp, _ll, _vp, _ll, _i]),
-    "frb_identity_scores": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "frb_identity_scores": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp]),
     "frb_match_identities": (_i, [_vp, _vp, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "frb_aggregate_templates": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "frb_track_consensus": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, C.c_double, _i, C.c_double, _vp, _vp]),
+    "frb_best_frames": (_i, [_vp, _vp, _vp, _vp, _i, C.c_double, _vp, _vp, _vp, _vp]),
     "frb_match": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "frb_match_last_flagged": (_i, [_vp]),
     "frb_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "frb_topk_merge_packed": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "frb_match_packed": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp]),
+    "frb_xchg_create": (_i, [_vp, _i, _i, _i, _i, _vp]),
+    "frb_xchg_connect": (_i, [_vp, _vp]),
+    "frb_xchg_status": (_i, [_vp]),
+    "frb_xchg_local_buffer": (_vp, [_vp]),
+    "frb_xchg_connect_local": (_i, [_vp, _i, _vp]),
+    "frb_match_sharded": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
     "frb_prefetch_host": (_i, [_vp, _vp, _i, _i]),
     "frb_embed_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "frb_match_host": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
@@ -143,6 +155,16 @@ class Context:
                 "this package has no CPU or other-GPU fallback")
         self.handle = h
         self.device = int(device)
+        # Wrappers that share this ctx (embedders, galleries) hold the lock across "is my upload still resident?" +
+        # the native call that relies on it, so another thread cannot swap the weights / gallery in between.
+        self.lock = threading.RLock()
+
+    def gallery_generation(self) -> int:
+        """Bumped by every frb_gallery_upload*: compare with the value read after one's own upload."""
+        return int(self._lib.frb_gallery_generation(self.handle))
+
+    def backbone_generation(self) -> int:
+        return int(self._lib.frb_backbone_generation(self.handle))
 
     def close(self):
         if getattr(self, "handle", None):

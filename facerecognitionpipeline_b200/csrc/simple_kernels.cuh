@@ -685,6 +685,67 @@ __device__ __forceinline__ bool cand_before(double sa, long long ia, double sb, 
   return ia < ib;
 }
 
+// ---- identity-sharded galleries: per-rank top-k rows travel to the peers' merge buffers over NVLink (peer memory)
+// One record of a per-rank top-k list as it is exchanged and merged: exact f64 score + global gallery id.
+struct alignas(16) TopkRec {
+  double score;
+  long long idx;
+};
+constexpr int kMaxPeers = 8;
+constexpr int kFlagStride = 32;   // flag words of different ranks sit 128 bytes apart
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Where the rows a kernel finishes go besides its local outputs.  world == 0: nowhere (single-GPU match).
+// Every producer kernel of a sharded match (finalize, exact fix-up, plain push) adds the rows it completed to
+// `done_rows`; the block that completes row number P raises this rank's flag word on every peer (epoch value), after
+// which the peers' merge kernels may read the slot.  slot[g] / flag[g] are addresses inside peer g's exchange buffer
+// (cudaIpc mapping; g == rank is the local buffer).
+struct PeerPush {
+  int world;
+  int rank;
+  unsigned epoch;
+  int P;                       // rows of this match (all probes of all ranks)
+  int* done_rows;              // local counter, zeroed at the start of the match
+  TopkRec* slot[kMaxPeers];    // [P][k] records of THIS rank inside peer g's buffer (current epoch parity)
+  unsigned* flag[kMaxPeers];   // this rank's result flag inside peer g's buffer
+};
+
+// n rows of this block are complete (their remote stores fenced by the storing threads, then __syncthreads)
+__device__ __forceinline__ void peer_rows_done(const PeerPush& pp, int n) {
+  __threadfence();
+  const int prev = atomicAdd(pp.done_rows, n);
+  if (prev + n == pp.P) {
+    __threadfence_system();
+    for (int g = 0; g < pp.world; ++g) st_release_sys(pp.flag[g], pp.epoch);
+  }
+}
+
+// threads t < k of a block hold record t of `row`; all threads of the block must call this
+__device__ __forceinline__ void peer_push_row(const PeerPush& pp, int row, int k, int t, double score, long long gid) {
+  if (t < k) {
+    TopkRec r;
+    r.score = score;
+    r.idx = gid;
+    for (int g = 0; g < pp.world; ++g) pp.slot[g][static_cast<size_t>(row) * k + t] = r;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (t == 0) peer_rows_done(pp, 1);
+}
+
 constexpr int kRescore = 64;       // survivors re-scored exactly per probe
 constexpr int kMaxCandPad = 2048;  // >= slices * kCand, power of two
 
@@ -703,6 +764,9 @@ struct FinalizeParams {
   float* out_score_f32;      // [P][k]
   unsigned char* out_accept; // [P]  top-1 score >= thr
   int* flagged;              // [P] 1 = proof failed -> exact scan required
+  int* flag_rows;            // compacted list of the flagged rows (order unspecified) ...
+  int* flag_count;           // ... and its length (device counter, zeroed at the start of the match)
+  PeerPush push;             // sharded match: proven rows go straight to the peers
 };
 
 // one block (128 threads) per probe
@@ -714,6 +778,7 @@ match_finalize_kernel(const FinalizeParams p) {
   __shared__ double s_ex[kRescore];
   __shared__ long long s_exi[kRescore];
   __shared__ float s_excl;
+  __shared__ int s_flag;
   const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int C = p.slices * kCand;
   int Cp = 64;
@@ -879,6 +944,15 @@ match_finalize_kernel(const FinalizeParams p) {
       }
     }
     p.flagged[row] = flag;
+    s_flag = flag;
+    if (flag) p.flag_rows[atomicAdd(p.flag_count, 1)] = row;   // the exact fix-up kernels take it from here
+  }
+  if (p.push.world > 0) {
+    __syncthreads();
+    if (!s_flag) {   // block-uniform
+      const long long gi = t < p.k ? s_exi[t] : -1;
+      peer_push_row(p.push, row, p.k, t, gi >= 0 ? s_ex[t] : -INFINITY, gi >= 0 ? gi + p.first_global_id : -1);
+    }
   }
 }
 
@@ -961,6 +1035,153 @@ match_exact_topk_kernel(const double* __restrict__ scores, long long N, const in
       break;
     }
   }
+}
+
+// ---- exact fix-up of the rows whose filter proof failed, without a host round trip: both kernels are launched
+// unconditionally after match_finalize_kernel and read the number of listed rows from the device counter it filled
+// (grid-stride over the list, immediate exit when it is empty).  No dense [rows][N] score buffer: every block keeps the
+// best k of its share of the gallery, the second kernel merges the kExactBlocks partial lists of a row.
+constexpr int kExactBlocks = 74;   // gallery partitions per listed row (grid.x of the partial kernel)
+constexpr int kExactRowsY = 16;    // listed rows in flight (grid.y): they share each gallery row through L2
+constexpr int kExactMaxK = 32;
+
+struct ExactFixParams {
+  const float* gallery; long long N;
+  const float* probes;          // [P][512] normalised probes
+  const int* rows;              // listed probe rows
+  const int* count;             // number of listed rows (device)
+  int k; float thr; long long first_global_id;
+  TopkRec* part;                // [P][kExactBlocks][k] scratch, indexed by list position (idx = local row, -1 = none)
+  double* out_score; long long* out_idx; float* out_score_f32; unsigned char* out_accept;
+  PeerPush push;
+};
+
+__global__ void __launch_bounds__(256)
+match_exact_part_kernel(const ExactFixParams p) {
+  __shared__ float s_probe[512];
+  __shared__ double w_sc[8][kExactMaxK];
+  __shared__ long long w_ix[8][kExactMaxK];
+  const int count = *p.count;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, k = p.k;
+  for (int f = blockIdx.y; f < count; f += gridDim.y) {
+    const int prow = p.rows[f];
+    __syncthreads();   // the previous row's merge has read the lists
+    for (int i = threadIdx.x; i < 512; i += 256) s_probe[i] = p.probes[static_cast<size_t>(prow) * 512 + i];
+    for (int i = threadIdx.x; i < 8 * kExactMaxK; i += 256) {
+      (&w_sc[0][0])[i] = -INFINITY;
+      (&w_ix[0][0])[i] = -1;
+    }
+    __syncthreads();
+    for (long long g = static_cast<long long>(blockIdx.x) * 8 + warp; g < p.N; g += static_cast<long long>(gridDim.x) * 8) {
+      const double s = warp_dot512_f64(p.gallery + g * 512, s_probe, lane);
+      if (lane == 0 && cand_before(s, g, w_sc[warp][k - 1], w_ix[warp][k - 1])) {
+        int j = k - 1;   // sorted insertion (canonical order); rare once the list has settled
+        while (j > 0 && cand_before(s, g, w_sc[warp][j - 1], w_ix[warp][j - 1])) {
+          w_sc[warp][j] = w_sc[warp][j - 1];
+          w_ix[warp][j] = w_ix[warp][j - 1];
+          --j;
+        }
+        w_sc[warp][j] = s;
+        w_ix[warp][j] = g;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // 8-way merge of the sorted warp lists -> this block's best k
+      int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      TopkRec* dst = p.part + (static_cast<size_t>(f) * gridDim.x + blockIdx.x) * k;
+      for (int r = 0; r < k; ++r) {
+        int bw = -1;
+        for (int w = 0; w < 8; ++w)
+          if (head[w] < k && w_ix[w][head[w]] >= 0 &&
+              (bw < 0 || cand_before(w_sc[w][head[w]], w_ix[w][head[w]], w_sc[bw][head[bw]], w_ix[bw][head[bw]])))
+            bw = w;
+        TopkRec rec;
+        rec.score = bw >= 0 ? w_sc[bw][head[bw]] : -INFINITY;
+        rec.idx = bw >= 0 ? w_ix[bw][head[bw]] : -1;
+        if (bw >= 0) ++head[bw];
+        dst[r] = rec;
+      }
+    }
+  }
+}
+
+// merge of a listed row's kExactBlocks partial lists: k rounds of block arg-max in canonical order (as
+// match_exact_topk_kernel), outputs for the probe row, and - sharded - the row goes to the peers
+__global__ void __launch_bounds__(128)
+match_exact_fix_kernel(const ExactFixParams p, int parts) {
+  __shared__ double s_best[128];
+  __shared__ long long s_besti[128];
+  __shared__ double s_out[kExactMaxK];
+  __shared__ long long s_outi[kExactMaxK];
+  const int count = *p.count;
+  const int t = threadIdx.x, k = p.k;
+  for (int f = blockIdx.x; f < count; f += gridDim.x) {
+    const int prow = p.rows[f];
+    const TopkRec* cand = p.part + static_cast<size_t>(f) * parts * k;
+    const int C = parts * k;
+    double pv = INFINITY;
+    long long pi = -1;
+    for (int r = 0; r < k; ++r) {
+      double best = -INFINITY;
+      long long besti = -1;
+      for (int c = t; c < C; c += 128) {
+        const TopkRec rec = cand[c];
+        if (rec.idx < 0) continue;
+        const bool after = (pi < 0) ? true : ((rec.score < pv) || (rec.score == pv && rec.idx > pi));
+        if (after && cand_before(rec.score, rec.idx, best, besti)) {
+          best = rec.score;
+          besti = rec.idx;
+        }
+      }
+      s_best[t] = best;
+      s_besti[t] = besti;
+      __syncthreads();
+      for (int o = 64; o > 0; o >>= 1) {
+        if (t < o && cand_before(s_best[t + o], s_besti[t + o], s_best[t], s_besti[t])) {
+          s_best[t] = s_best[t + o];
+          s_besti[t] = s_besti[t + o];
+        }
+        __syncthreads();
+      }
+      pv = s_best[0];
+      pi = s_besti[0];
+      if (t == 0) {
+        s_out[r] = pi >= 0 ? pv : -INFINITY;
+        s_outi[r] = pi >= 0 ? pi + p.first_global_id : -1;
+      }
+      __syncthreads();
+      if (pi < 0) {   // gallery exhausted (block-uniform)
+        if (t == 0)
+          for (int r2 = r + 1; r2 < k; ++r2) {
+            s_out[r2] = -INFINITY;
+            s_outi[r2] = -1;
+          }
+        break;
+      }
+    }
+    __syncthreads();
+    if (t < k) {
+      const size_t o = static_cast<size_t>(prow) * k + t;
+      p.out_idx[o] = s_outi[t];
+      p.out_score[o] = s_out[t];
+      p.out_score_f32[o] = static_cast<float>(s_out[t]);
+    }
+    if (t == 0) p.out_accept[prow] = (s_outi[0] >= 0 && static_cast<float>(s_out[0]) >= p.thr) ? 1 : 0;
+    if (p.push.world > 0) peer_push_row(p.push, prow, k, t, t < k ? s_out[t] : 0.0, t < k ? s_outi[t] : -1);
+    __syncthreads();
+  }
+}
+
+// constant rows for an empty gallery (idx -1, score -inf, accept 0)
+__global__ void match_fill_empty_kernel(int P, int k, double* __restrict__ out_score, long long* __restrict__ out_idx,
+                                        float* __restrict__ out_score_f32, unsigned char* __restrict__ out_accept) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P * k) {
+    out_idx[i] = -1;
+    if (out_score) out_score[i] = -INFINITY;
+    out_score_f32[i] = -INFINITY;
+  }
+  if (i < P) out_accept[i] = 0;
 }
 
 // ------------------------------------------------------------------ per-identity matching over gallery SAMPLES
@@ -1220,12 +1441,154 @@ track_consensus_kernel(const long long* __restrict__ top_idx, const float* __res
   out[t] = r;
 }
 
-// merge G per-rank top-k lists (after an all-gather) into the global top-k; one thread per probe.
-// in_score/in_idx: [G][P][k]
-__global__ void topk_merge_kernel(const double* __restrict__ in_score, const long long* __restrict__ in_idx, int G,
-                                  int P, int k, float thr, double* __restrict__ out_score,
-                                  long long* __restrict__ out_idx, float* __restrict__ out_score_f32,
-                                  unsigned char* __restrict__ out_accept) {
+// ------------------------------------------------------------------ server best-frame selection
+// LiveRecognitionTracker.get_best_frame + the should_recognize gate (face_recognition_server.py:39-85) for T tracks:
+// quality = det * min(blur / 100, 1) in f64 as Python evaluates it; Python's max() keeps the FIRST maximal frame;
+// ready = best frame's det_score > min_det.  One warp per track.
+__global__ void __launch_bounds__(128)
+best_frames_kernel(const double* __restrict__ det, const double* __restrict__ blur, const long long* __restrict__ seg,
+                   int T, double min_det, long long* __restrict__ out_idx, double* __restrict__ out_quality,
+                   unsigned char* __restrict__ out_ready) {
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const long long f0 = seg[t], f1 = seg[t + 1];
+  double best = 0.0;
+  long long besti = -1;
+  for (long long f = f0 + lane; f < f1; f += 32) {
+    const double q = __dmul_rn(det[f], fmin(__ddiv_rn(blur[f], 100.0), 1.0));
+    if (besti < 0 || q > best) {   // strictly greater: the earliest frame of this lane's stride wins a tie
+      best = q;
+      besti = f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (oi >= 0 && (besti < 0 || ob > best || (ob == best && oi < besti))) {
+      best = ob;
+      besti = oi;
+    }
+  }
+  if (lane == 0) {
+    out_idx[t] = besti >= 0 ? besti - f0 : -1;
+    if (out_quality) out_quality[t] = besti >= 0 ? best : 0.0;
+    out_ready[t] = (besti >= 0 && det[besti] > min_det) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------ identity-sharded gallery: exchange + merge
+// (new work, no reference counterpart: the reference is single-device)
+struct XchgWait {
+  int world;                       // 0 = nothing to wait for
+  unsigned epoch;
+  const unsigned* flag;            // [world] flag words (kFlagStride apart) in the LOCAL exchange buffer, raised by the peers
+  unsigned long long timeout_ns;
+  int* status;                     // pinned host word: set to rank+1 of the first missing peer before trapping
+};
+
+// lanes 0..world-1 of the calling warp poll one peer flag each (acquire at system scope)
+__device__ __forceinline__ void xchg_wait_flags(const XchgWait& w, int lane) {
+  if (lane < w.world) {
+    const unsigned long long t0 = global_timer_ns();
+    while (static_cast<int>(ld_acquire_sys(w.flag + lane * kFlagStride) - w.epoch) < 0) {
+      __nanosleep(200);
+      if (global_timer_ns() - t0 > w.timeout_ns) {   // a peer never arrived: fail loudly instead of hanging the GPU
+        if (w.status) *reinterpret_cast<volatile int*>(w.status) = lane + 1;
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// one warp: returns when every peer's probes of this epoch have landed in the local buffer; the kernels launched
+// after it (filter: TMA loads) then read them
+__global__ void xchg_wait_kernel(const XchgWait w) { xchg_wait_flags(w, threadIdx.x); }
+
+// q = q / (||q|| + 1e-8) as probe_prepare_kernel, written to row (row0 + b) of EVERY rank's probe buffers
+struct ProbePush {
+  int world;
+  int row0;                        // first global probe row of this rank
+  int rows;                        // local rows (== gridDim.x)
+  unsigned epoch;
+  int* done_rows;
+  float* f32[kMaxPeers];           // [P][512] inside peer g's exchange buffer
+  __nv_bfloat16* bf16[kMaxPeers];
+  unsigned* flag[kMaxPeers];       // this rank's probe flag inside peer g's buffer
+};
+
+__global__ void __launch_bounds__(128)
+probe_push_kernel(const float* __restrict__ in, int normalize, const ProbePush pp) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  __shared__ float red[4];
+  // same element-to-thread mapping and summation order as probe_prepare_kernel: a probe normalises to the same bits
+  // whether it is matched against the whole gallery or a shard
+  float x[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) x[j] = in[static_cast<size_t>(b) * 512 + t + 128 * j];
+  if (normalize) {
+    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((t & 31) == 0) red[t >> 5] = ss;
+    __syncthreads();
+    const float n2 = sqrtf(red[0] + red[1] + red[2] + red[3]) + 1e-8f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = x[j] / n2;
+  }
+  for (int g = 0; g < pp.world; ++g) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t o = static_cast<size_t>(pp.row0 + b) * 512 + t + 128 * j;
+      pp.f32[g][o] = x[j];
+      pp.bf16[g][o] = __float2bfloat16_rn(x[j]);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    if (atomicAdd(pp.done_rows, 1) + 1 == pp.rows) {
+      __threadfence_system();
+      for (int g = 0; g < pp.world; ++g) st_release_sys(pp.flag[g], pp.epoch);
+    }
+  }
+}
+// a rank without probes of its own still has to raise its flags
+__global__ void probe_push_empty_kernel(const ProbePush pp) {
+  if (threadIdx.x == 0)
+    for (int g = 0; g < pp.world; ++g) st_release_sys(pp.flag[g], pp.epoch);
+}
+
+// local [P][k] results (dense exact path, empty shard) -> the peers
+__global__ void __launch_bounds__(128)
+xchg_push_rows_kernel(const double* __restrict__ score, const long long* __restrict__ idx, int P, int k, const PeerPush pp) {
+  const int row0 = blockIdx.x * 32;
+  const int nrows = min(32, P - row0);
+  for (int i = threadIdx.x; i < nrows * k; i += blockDim.x) {
+    TopkRec r;
+    r.score = score[static_cast<size_t>(row0) * k + i];
+    r.idx = idx[static_cast<size_t>(row0) * k + i];
+    for (int g = 0; g < pp.world; ++g) pp.slot[g][static_cast<size_t>(row0) * k + i] = r;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) peer_rows_done(pp, nrows);
+}
+
+// merge G per-rank top-k lists into the global top-k in canonical order; one thread per probe.  in: [G][P][k]
+// records.  With wait.world > 0 the lists are the slots of the local exchange buffer and the first warp of every
+// block first waits for the peers' result flags.
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(const TopkRec* __restrict__ in, int G, int P, int k, float thr, double* __restrict__ out_score,
+                  long long* __restrict__ out_idx, float* __restrict__ out_score_f32,
+                  unsigned char* __restrict__ out_accept, const XchgWait wait) {
+  if (wait.world > 0) {
+    if (threadIdx.x < 32) xchg_wait_flags(wait, threadIdx.x);
+    __syncthreads();
+  }
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= P) return;
   double ps = INFINITY;
@@ -1235,30 +1598,42 @@ __global__ void topk_merge_kernel(const double* __restrict__ in_score, const lon
     long long besti = -1;
     for (int g = 0; g < G; ++g)
       for (int j = 0; j < k; ++j) {
-        const size_t o = (static_cast<size_t>(g) * P + row) * k + j;
-        const double v = in_score[o];
-        const long long ix = in_idx[o];
-        if (ix < 0) continue;
-        const bool after = (pi < 0) ? true : ((v < ps) || (v == ps && ix > pi));
-        if (after && cand_before(v, ix, best, besti)) {
-          best = v;
-          besti = ix;
+        const TopkRec rec = in[(static_cast<size_t>(g) * P + row) * k + j];
+        if (rec.idx < 0) continue;
+        const bool after = (pi < 0) ? true : ((rec.score < ps) || (rec.score == ps && rec.idx > pi));
+        if (after && cand_before(rec.score, rec.idx, best, besti)) {
+          best = rec.score;
+          besti = rec.idx;
         }
       }
     const size_t o = static_cast<size_t>(row) * k + r;
     out_idx[o] = besti;
-    out_score[o] = besti >= 0 ? best : -INFINITY;
+    if (out_score) out_score[o] = besti >= 0 ? best : -INFINITY;
     out_score_f32[o] = besti >= 0 ? static_cast<float>(best) : -INFINITY;
     if (r == 0) out_accept[row] = (besti >= 0 && static_cast<float>(best) >= thr) ? 1 : 0;
     if (besti < 0) {
       for (int r2 = r + 1; r2 < k; ++r2) {
         const size_t o2 = static_cast<size_t>(row) * k + r2;
-        out_idx[o2] = -1; out_score[o2] = -INFINITY; out_score_f32[o2] = -INFINITY;
+        out_idx[o2] = -1;
+        if (out_score) out_score[o2] = -INFINITY;
+        out_score_f32[o2] = -INFINITY;
       }
       break;
     }
     ps = best;
     pi = besti;
+  }
+}
+
+// separate score / id arrays (frb_topk_merge's layout) -> records
+__global__ void topk_pack_kernel(const double* __restrict__ score, const long long* __restrict__ idx, size_t n,
+                                 TopkRec* __restrict__ out) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    TopkRec r;
+    r.score = score[i];
+    r.idx = idx[i];
+    out[i] = r;
   }
 }
 

@@ -86,8 +86,9 @@ class FaceEmbedder:
             state_dict = weights.load_checkpoint_state_dict(model_path)
         self._program = weights.build_program(state_dict, architecture, layout)
         self._ctx = _native.default_context(index)
-        self._program.load_into(self._ctx)
-        self._ctx.backbone_token = id(self)
+        with self._ctx.lock:
+            self._program.load_into(self._ctx)
+            self._loaded_gen = self._ctx.backbone_generation()
         self._flags = _native.FRB_EMBED_L2 if layout == "adaface" else 0
         self.input_size = (112, 112)
         self.is_onnx = False
@@ -134,21 +135,24 @@ class FaceEmbedder:
         return groups, order
 
     def _ensure_loaded(self):
-        if getattr(self._ctx, "backbone_token", None) != id(self):
+        """Reload this embedder's program when anything else was loaded into the shared context since
+        (`frb_backbone_generation` counts the loads).  Call with the context's lock held."""
+        if self._loaded_gen != self._ctx.backbone_generation():
             self._program.load_into(self._ctx)
-            self._ctx.backbone_token = id(self)
+            self._loaded_gen = self._ctx.backbone_generation()
 
     def _embed_u8(self, stack: np.ndarray, S: int, normalize: bool) -> np.ndarray:
-        self._ensure_loaded()
         n = len(stack)
         out = np.empty((n, 512), np.float32)
         flags = self._flags | (_native.FRB_EMBED_RENORM if normalize else 0)
         chunks = [np.ascontiguousarray(stack[i:i + self.max_batch]) for i in range(0, n, self.max_batch)]
-        for j, chunk in enumerate(chunks):
-            if j + 1 < len(chunks):   # the next chunk's crops travel while this one computes
-                self._ctx.frb_prefetch_host(chunks[j + 1].ctypes.data, len(chunks[j + 1]), S)
-            dst = out[j * self.max_batch:j * self.max_batch + len(chunk)]
-            self._ctx.frb_embed_host(chunk.ctypes.data, len(chunk), S, flags, dst.ctypes.data, None)
+        with self._ctx.lock:   # check + calls are one unit: no other embedder may swap the weights in between
+            self._ensure_loaded()
+            for j, chunk in enumerate(chunks):
+                if j + 1 < len(chunks):   # the next chunk's crops travel while this one computes
+                    self._ctx.frb_prefetch_host(chunks[j + 1].ctypes.data, len(chunks[j + 1]), S)
+                dst = out[j * self.max_batch:j * self.max_batch + len(chunk)]
+                self._ctx.frb_embed_host(chunk.ctypes.data, len(chunk), S, flags, dst.ctypes.data, None)
         return out
 
     # ------------------------------------------------------------------ embedding API

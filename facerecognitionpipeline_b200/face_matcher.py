@@ -103,6 +103,46 @@ def consensus_on_device(top_idx, top_score, frames_per_track, similarity_thresho
     return out.cpu().numpy().view(dt).reshape(T)
 
 
+BEST_FRAME_MIN_DET = 0.6   # face_recognition_server.py:61: the best frame's detection score must exceed this
+
+
+def best_frame_index(det_scores, blur_scores) -> Tuple[int, bool]:
+    """Server best-frame selection for ONE track (LiveRecognitionTracker.get_best_frame / should_recognize,
+    face_recognition_server.py:39-85): quality = det_score * min(blur_score / 100, 1); the FIRST frame with the
+    largest quality wins (Python `max`); the track is ready for recognition when that frame's det_score > 0.6.
+    A frame without quality metrics counts with blur_score 0."""
+    best, best_q = -1, 0.0
+    for i, (d, b) in enumerate(zip(det_scores, blur_scores)):
+        q = float(d) * min(float(b) / 100.0, 1.0)
+        if best < 0 or q > best_q:
+            best, best_q = i, q
+    return best, bool(best >= 0 and float(det_scores[best]) > BEST_FRAME_MIN_DET)
+
+
+def best_frames_batch(det_scores, blur_scores, seg, device: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """Same rule for T tracks in one launch (`frb_best_frames`): track t owns frames [seg[t], seg[t+1]).
+    Returns (index of the best frame inside its track [T] i64 (-1 = empty track), ready [T] bool)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _native
+    seg = np.ascontiguousarray(seg, dtype=np.int64)
+    T = len(seg) - 1
+    if T <= 0:
+        return np.zeros((0,), np.int64), np.zeros((0,), bool)
+    dev = torch.device("cuda", device)
+    d = torch.from_numpy(np.ascontiguousarray(det_scores, dtype=np.float64)).to(dev)
+    b = torch.from_numpy(np.ascontiguousarray(blur_scores, dtype=np.float64)).to(dev)
+    s = torch.from_numpy(seg).to(dev)
+    idx = torch.empty((T,), dtype=torch.int64, device=dev)
+    ready = torch.empty((T,), dtype=torch.uint8, device=dev)
+    ctx = _native.default_context(device)
+    ctx.frb_best_frames(d.data_ptr(), b.data_ptr(), s.data_ptr(), T, BEST_FRAME_MIN_DET, idx.data_ptr(), None,
+                        ready.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    return idx.cpu().numpy(), ready.cpu().numpy().astype(bool)
+
+
 class FaceMatcher:
     def __init__(self, gallery_path=None, similarity_threshold=0.5, aggregation_method="majority_vote",
                  model_type="adaface", architecture="ir_101", embedder: Optional[FaceEmbedder] = None,

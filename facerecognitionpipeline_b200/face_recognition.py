@@ -7,13 +7,16 @@ fixed-point warpAffine, optionally fused with the BGR normalisation into the NHW
 backbone consumes.  The 2x3 matrix still comes from cv2.estimateAffinePartial2D on the host
 (RANSAC + LM refine on 5 points, microseconds) so that the matrix is the reference's own.
 
-Face detection / quality filtering (insightface buffalo_l, face_recognition.py:19-48,77-216) are out of
-scope: `FaceProcessor` here only wires a caller-supplied detector to the aligner.
+Face detection (insightface buffalo_l, face_recognition.py:19-48) is out of scope: `FaceProcessor`
+takes a caller-supplied detector.  `FaceQualityFilter` (face_recognition.py:77-158) is host glue between detector and
+embedder that decides WHICH crops reach the hot path (enrollment drops blurred / profile / tiny faces through it), so
+it is kept with the reference's arithmetic and ordering, pinned by the reference's own outputs
+(tests/golden/make_golden_r2.py).
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -85,9 +88,62 @@ class FaceAligner:
         return self.align_batch(image, [landmarks], method)[0][0]
 
 
+class FaceQualityFilter:
+    """Same gates, same order, same metrics dict as the reference (face_recognition.py:77-158): detection score, face
+    size = min(bbox width, height), yaw / pitch / roll estimated from the 5 landmarks, Laplacian-variance blur score
+    of the ALIGNED crop.  The metrics dict only holds what was computed before the first failing gate - callers sort by
+    `quality_metrics.get('blur_score', 1000)`, so which keys exist is observable."""
+
+    def __init__(self, min_det_score=0.6, min_face_size=60, max_yaw=45, max_pitch=30, max_roll=30, check_blur=True,
+                 blur_threshold=100):
+        self.min_det_score = min_det_score
+        self.min_face_size = min_face_size
+        self.max_yaw, self.max_pitch, self.max_roll = max_yaw, max_pitch, max_roll
+        self.check_blur = check_blur
+        self.blur_threshold = blur_threshold
+
+    def compute_blur_score(self, face_image: np.ndarray) -> float:
+        import cv2
+        gray = cv2.cvtColor(face_image, cv2.COLOR_RGB2GRAY) if face_image.ndim == 3 else face_image
+        return cv2.Laplacian(gray, cv2.CV_64F).var()
+
+    def compute_pose_angles(self, landmarks: np.ndarray) -> Dict[str, float]:
+        # landmark order: left eye, right eye, nose, left mouth corner, right mouth corner; arithmetic stays in the
+        # array's own dtype (f32 from the detector) exactly as the reference's expressions evaluate
+        eye_l, eye_r, nose, mouth_l, mouth_r = (landmarks[i] for i in range(5))
+        eyes_mid = (eye_l + eye_r) / 2
+        eyes_vec = eye_r - eye_l
+        roll = np.degrees(np.arctan2(eyes_vec[1], eyes_vec[0]))
+        dx = nose[0] - eyes_mid[0]
+        yaw = np.degrees(np.arcsin(np.clip(dx / np.linalg.norm(eyes_vec), -1, 1))) * 2
+        mouth_mid = (mouth_l + mouth_r) / 2
+        pitch = ((nose[1] - eyes_mid[1]) / (mouth_mid[1] - eyes_mid[1]) - 0.5) * 60
+        return {"yaw": yaw, "pitch": pitch, "roll": roll}
+
+    def is_valid(self, face_dict: Dict, face_image: Optional[np.ndarray] = None) -> Tuple[bool, Dict]:
+        metrics: Dict = {"det_score": face_dict["det_score"]}
+        if metrics["det_score"] < self.min_det_score:
+            return False, metrics
+        x1, y1, x2, y2 = (face_dict["bbox"][i] for i in range(4))
+        metrics["face_size"] = min(x2 - x1, y2 - y1)
+        if metrics["face_size"] < self.min_face_size:
+            return False, metrics
+        pose = self.compute_pose_angles(face_dict["landmarks"])
+        metrics.update(pose)
+        for key, limit in (("yaw", self.max_yaw), ("pitch", self.max_pitch), ("roll", self.max_roll)):
+            if abs(pose[key]) > limit:
+                return False, metrics
+        if self.check_blur and face_image is not None:
+            metrics["blur_score"] = self.compute_blur_score(face_image)
+            if metrics["blur_score"] < self.blur_threshold:
+                return False, metrics
+        return True, metrics
+
+
 class FaceProcessor:
-    """Detector wiring only.  `detector` must provide detect(image_rgb) -> list of dicts with
-    'bbox', 'landmarks', 'det_score' like the reference's FaceDetector (face_recognition.py:30-48)."""
+    """detect -> align (device warp, bit-exact vs cv2) -> quality filter -> sort, as face_recognition.py:160-216.
+    `detector` must provide detect(image_rgb) -> list of dicts with 'bbox', 'landmarks', 'det_score' like the
+    reference's FaceDetector (face_recognition.py:30-48); the reference's own detector (insightface) is out of scope."""
 
     def __init__(self, output_size=224, det_size=(640, 640), det_thresh=0.5, quality_filter_config: Optional[Dict] = None,
                  providers=None, detector=None):
@@ -96,6 +152,7 @@ class FaceProcessor:
                               "is outside the B200 hot path); pass detector=...")
         self.detector = detector
         self.aligner = FaceAligner(output_size=output_size)
+        self.quality_filter = FaceQualityFilter(**(quality_filter_config or {}))
 
     def process_image(self, image_path: str, return_all: bool = False) -> List[Dict]:
         import cv2
@@ -108,9 +165,14 @@ class FaceProcessor:
         faces = self.detector.detect(image_rgb)
         if not faces:
             return []
-        aligned, _ = self.aligner.align_batch(image_rgb, [f["landmarks"] for f in faces])
-        results = [{"aligned_face": aligned[i], "bbox": f["bbox"], "landmarks": f["landmarks"],
-                    "det_score": f["det_score"], "quality_metrics": {"det_score": f["det_score"]}, "is_valid": True}
-                   for i, f in enumerate(faces)]
-        results.sort(key=lambda r: r["det_score"], reverse=True)
+        aligned, _ = self.aligner.align_batch(image_rgb, [f["landmarks"] for f in faces])   # all faces of the frame: one launch
+        results = []
+        for i, f in enumerate(faces):
+            ok, metrics = self.quality_filter.is_valid(f, aligned[i])
+            if ok or return_all:
+                results.append({"aligned_face": aligned[i], "bbox": f["bbox"], "landmarks": f["landmarks"],
+                                "det_score": f["det_score"], "quality_metrics": metrics, "is_valid": ok})
+        # stable sort, descending det_score x blur; a face rejected before the blur gate has no blur_score and
+        # counts as 1000 (face_recognition.py:206-209) - reproduced, it decides enrollment's top-max_faces selection
+        results.sort(key=lambda r: r["det_score"] * r["quality_metrics"].get("blur_score", 1000), reverse=True)
         return results if return_all else results[:1]

@@ -78,7 +78,8 @@ class GalleryManager:
         self.students: Dict[str, StudentRecord] = {}
         self._device = device
         self._ctx = None
-        self._version = 0
+        self._version = 0          # bumped by every mutation of self.students
+        self._resident = None      # (self._version, ctx gallery generation) after this object's last upload
         self._ids: List[str] = []
 
         os.makedirs(os.path.dirname(gallery_path) or ".", exist_ok=True)
@@ -161,34 +162,36 @@ class GalleryManager:
         return self._ctx
 
     def _ensure_resident(self):
-        """Upload the template matrix if the student set changed since the last upload (or another
-        GalleryManager took over the context's resident gallery)."""
+        """Upload the template matrix if the student set changed since the last upload, or anything else was
+        uploaded to the shared context in between (the ctx counts its uploads: `frb_gallery_generation`).
+        Call with the context's lock held."""
         ctx = self._context()
-        token = (id(self), self._version, len(self.students))
-        if getattr(ctx, "gallery_token", None) == token:
+        if self._resident == (self._version, ctx.gallery_generation()):
             return
         mat, ids = self.get_gallery_embeddings()
         mat = np.ascontiguousarray(mat, dtype=np.float32).reshape(len(ids), 512)
         ctx.frb_gallery_upload(mat.ctypes.data, len(ids), 0, 0)
         self._ids = ids
-        ctx.gallery_token = token
+        self._resident = (self._version, ctx.gallery_generation())
 
     def search_batch(self, query_embeddings: np.ndarray, top_k: int = 5, threshold: float = 0.0):
         """Match P probes at once. Returns (results, accept) where results[p] is the `search` list for
-        probe p and accept[p] = (top-1 score >= threshold)."""
+        probe p and accept[p] = (top-1 score >= threshold).  Any top_k >= 1 like the reference
+        (gallery_manager.py:197): rows come back as min(top_k, N) tuples."""
         q = np.ascontiguousarray(query_embeddings, dtype=np.float32).reshape(-1, 512)
         P = len(q)
         if len(self.students) == 0 or P == 0:
             return [[] for _ in range(P)], np.zeros(P, dtype=bool)
-        if int(top_k) > 32:
-            raise ValueError("top_k > 32 is not supported by the device matcher")
-        self._ensure_resident()
-        k = int(top_k)
+        k = max(1, min(int(top_k), len(self.students)))
         scores = np.empty((P, k), np.float32)
         idx = np.empty((P, k), np.int64)
         acc = np.empty((P,), np.uint8)
-        self._context().frb_match_host(q.ctypes.data, P, k, float(threshold), 1, scores.ctypes.data, idx.ctypes.data,
-                                       acc.ctypes.data)
+        ctx = self._context()
+        with ctx.lock:
+            self._ensure_resident()
+            ids = self._ids
+            ctx.frb_match_host(q.ctypes.data, P, k, float(threshold), 1, scores.ctypes.data, idx.ctypes.data,
+                               acc.ctypes.data)
         out = []
         for p in range(P):
             row = []
@@ -196,7 +199,7 @@ class GalleryManager:
                 gi = int(idx[p, j])
                 if gi < 0:
                     break
-                sid = self._ids[gi]
+                sid = ids[gi]
                 row.append((sid, self.students[sid].name, float(scores[p, j])))
             out.append(row)
         return out, acc.astype(bool)

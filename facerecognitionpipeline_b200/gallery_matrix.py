@@ -72,7 +72,7 @@ class MatrixGallery:
         base, extra = divmod(self.num_students, world)          # same contiguous balanced shards as dist.shard_bounds
         self.lo = rank * base + min(rank, extra)
         self.hi = self.lo + base + (1 if rank < extra else 0)
-        self._device, self._ctx, self._chunk = device, None, chunk_rows
+        self._device, self._ctx, self._chunk, self._gen = device, None, chunk_rows, None
         if upload:
             self.upload()
 
@@ -94,13 +94,13 @@ class MatrixGallery:
             stage[: r1 - r0].numpy()[...] = self.templates[self.lo + r0:self.lo + r1]     # page-in from the map
             buf[r0:r1].copy_(stage[: r1 - r0], non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()                                    # stage is reused
-        self._ctx.frb_gallery_upload(buf.data_ptr(), n, self.lo, 1)
-        self._ctx.gallery_token = ("matrix", id(self))
+        with self._ctx.lock:
+            self._ctx.frb_gallery_upload(buf.data_ptr(), n, self.lo, 1)
+            self._gen = self._ctx.gallery_generation()
 
     def search_batch(self, query_embeddings: np.ndarray, top_k: int = 5, threshold: float = 0.0):
         """Same contract as GalleryManager.search_batch: ([[(student_id, name, score)]], accept[P]) over this shard."""
-        if self._ctx is None or getattr(self._ctx, "gallery_token", None) != ("matrix", id(self)):
-            self.upload()
+        from . import _native
         q = np.ascontiguousarray(query_embeddings, dtype=np.float32).reshape(-1, 512)
         P, k = len(q), int(top_k)
         if P == 0 or self.hi == self.lo:
@@ -108,7 +108,11 @@ class MatrixGallery:
         scores = np.empty((P, k), np.float32)
         idx = np.empty((P, k), np.int64)
         acc = np.empty((P,), np.uint8)
-        self._ctx.frb_match_host(q.ctypes.data, P, k, float(threshold), 1, scores.ctypes.data, idx.ctypes.data, acc.ctypes.data)
+        ctx = self._ctx or _native.default_context(self._device)
+        with ctx.lock:
+            if self._ctx is None or self._gen != ctx.gallery_generation():   # something else took the context's gallery
+                self.upload()
+            ctx.frb_match_host(q.ctypes.data, P, k, float(threshold), 1, scores.ctypes.data, idx.ctypes.data, acc.ctypes.data)
         out: List[List[Tuple[str, str, float]]] = []
         for p in range(P):
             row = []

@@ -44,18 +44,24 @@ class IdentityGallery:
             n = np.linalg.norm(self.samples.astype(np.float64), axis=1)
             if np.abs(n - 1.0).max() > 1e-3:
                 raise ValueError("gallery samples must be L2-normalised embeddings (FaceEmbedder output)")
-        self._device, self._ctx = device, None
+        self._device, self._ctx, self._gen = device, None, None
 
     # ---- device plumbing
-    def _resident(self):
+    def _context(self):
         from . import _native
         if self._ctx is None:
             self._ctx = _native.default_context(self._device)
-        if getattr(self._ctx, "gallery_token", None) != ("samples", id(self)):
-            self._ctx.frb_gallery_upload_samples(self.samples.ctypes.data, len(self.samples), self.seg.ctypes.data,
-                                                 len(self.names), 0)
-            self._ctx.gallery_token = ("samples", id(self))
         return self._ctx
+
+    def _resident(self):
+        """Upload the samples unless this object's upload is still the context's resident gallery (the ctx counts
+        uploads: `frb_gallery_generation`; object identity is NOT used, ids are recycled).  Lock held by the caller."""
+        ctx = self._context()
+        if self._gen is None or self._gen != ctx.gallery_generation():
+            ctx.frb_gallery_upload_samples(self.samples.ctypes.data, len(self.samples), self.seg.ctypes.data,
+                                           len(self.names), 0)
+            self._gen = ctx.gallery_generation()
+        return ctx
 
     @staticmethod
     def _prepare(probes: np.ndarray) -> np.ndarray:
@@ -78,12 +84,14 @@ class IdentityGallery:
         P, S = len(q), len(self.names)
         if P == 0 or S == 0:
             return np.zeros((P, S), np.float32)
-        ctx = self._resident()
         dev = torch.device("cuda", self._device)
         d_q = torch.from_numpy(q).to(dev)
         out = torch.empty((P, S), dtype=torch.float32, device=dev)
-        ctx.frb_identity_scores(d_q.data_ptr(), P, 0, self._agg(aggregation), max(int(k), 1), out.data_ptr(),
-                                torch.cuda.current_stream(dev).cuda_stream)
+        with self._context().lock:
+            ctx = self._resident()
+            ctx.frb_identity_scores(d_q.data_ptr(), P, 0, self._agg(aggregation), max(int(k), 1), out.data_ptr(), S,
+                                    torch.cuda.current_stream(dev).cuda_stream)
+            torch.cuda.current_stream(dev).synchronize()
         return out.cpu().numpy()
 
     def rank_batch(self, probes: np.ndarray, top_k: int = 1, threshold: float = 0.0, aggregation: str = "mean",
@@ -97,15 +105,17 @@ class IdentityGallery:
         acc = np.zeros((P,), bool)
         if P == 0 or S == 0:
             return idx, sc, acc
-        ctx = self._resident()
         dev = torch.device("cuda", self._device)
         d_q = torch.from_numpy(q).to(dev)
         d_sc = torch.empty((P, K), dtype=torch.float32, device=dev)
         d_ix = torch.empty((P, K), dtype=torch.int64, device=dev)
         d_ac = torch.empty((P,), dtype=torch.uint8, device=dev)
-        ctx.frb_match_identities(d_q.data_ptr(), P, K, float(threshold), 0, self._agg(aggregation), max(int(k), 1),
-                                 d_sc.data_ptr(), d_ix.data_ptr(), d_ac.data_ptr(),
-                                 torch.cuda.current_stream(dev).cuda_stream)
+        with self._context().lock:
+            ctx = self._resident()
+            ctx.frb_match_identities(d_q.data_ptr(), P, K, float(threshold), 0, self._agg(aggregation), max(int(k), 1),
+                                     d_sc.data_ptr(), d_ix.data_ptr(), d_ac.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream)
+            torch.cuda.current_stream(dev).synchronize()
         return d_ix.cpu().numpy(), d_sc.cpu().numpy(), d_ac.cpu().numpy().astype(bool)
 
     def identify_batch(self, probes: np.ndarray, threshold: float, aggregation: str = "mean",

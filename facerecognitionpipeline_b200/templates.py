@@ -114,6 +114,5 @@ def aggregate_on_device(embeddings, counts, method: str = "mean", min_similarity
                                 float(min_similarity), out.data_ptr(), kept.data_ptr(), st)
     if upload_as_gallery and S:
         torch.cuda.current_stream(dev).synchronize()
-        ctx.frb_gallery_upload(out.data_ptr(), S, int(first_global_id), 1)
-        ctx.gallery_token = None
+        ctx.frb_gallery_upload(out.data_ptr(), S, int(first_global_id), 1)   # bumps the ctx's gallery generation
     return out, kept

@@ -98,6 +98,10 @@ int frb_embed_profile(frb_ctx* ctx, const void* d_in, int B, int flags, float* d
  * first_global_id is added to local row numbers in every result (identity-sharded galleries). */
 int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, long long first_global_id, int is_device);
 long long frb_gallery_size(frb_ctx* ctx);
+/* Residency generations: every frb_gallery_upload* / frb_backbone_load bumps the ctx's counter.  A wrapper that shares a
+ * ctx remembers the value after ITS upload and re-uploads when it no longer matches (replaces Python-side id() tokens). */
+long long frb_gallery_generation(frb_ctx* ctx);
+long long frb_backbone_generation(frb_ctx* ctx);
 /* ---- per-identity matching over a gallery of SAMPLES (evaluate_models_v2.ipynb cells 3-5: compute_all_similarities,
  * aggregate_max / aggregate_mean / aggregate_topk, identify_probe) ----
  * samples: [T][512] f32 rows (host or device); identity i owns rows [h_seg[i], h_seg[i+1]) (h_seg: S+1 int64 on the
@@ -105,9 +109,10 @@ long long frb_gallery_size(frb_ctx* ctx);
 int frb_gallery_upload_samples(frb_ctx* ctx, const float* samples, long long T, const long long* h_seg, long long S,
                                int is_device);
 /* identity_scores of identify_probe for P probes: d_out [P][S] f32; agg 0 = max, 1 = mean, 2 = mean of the agg_k best;
- * an identity without samples scores -1.  Probes are normalised like search() when normalize != 0. */
+ * an identity without samples scores -1.  Probes are normalised like search() when normalize != 0.
+ * S_expected: the identity count the caller sized d_out for (fails when another gallery is resident; < 0 = unchecked). */
 int frb_identity_scores(frb_ctx* ctx, const float* d_probes, int P, int normalize, int agg, int agg_k, float* d_out,
-                        void* stream);
+                        long long S_expected, void* stream);
 /* top-k identities per probe ranked by (score desc, identity index asc): scores f32 [P][k], idx i64 [P][k] (identity
  * indices, -1 = fewer than k identities), accept u8 [P] (best score >= thr).  Exact by construction: tensor-core
  * filter over the samples, exact f64 aggregates for the candidate identities, proof, exact scan for unproven rows. */
@@ -142,17 +147,50 @@ typedef struct frb_track_result {
 int frb_track_consensus(frb_ctx* ctx, const long long* d_top_idx, const float* d_top_score, int k_stride,
                         const long long* d_seg, int T, int max_frames, double min_quality, int min_frames,
                         double threshold, frb_track_result* d_out, void* stream);
+/* ---- server best-frame selection (LiveRecognitionTracker.get_best_frame and the should_recognize gate,
+ * face_recognition_server.py:39-85) for T tracks at once: track t owns frames [d_seg[t], d_seg[t+1]) (T+1 int64 on the
+ * device); quality = det_score * min(blur_score / 100, 1) in f64; the FIRST frame with the largest quality wins (Python
+ * max).  Outputs (device): best_idx i64 [T] (frame index inside the track, -1 = empty track), best_quality f64 [T]
+ * (optional), ready u8 [T] (the best frame's det_score > min_det; the reference uses 0.6). */
+int frb_best_frames(frb_ctx* ctx, const double* d_det, const double* d_blur, const long long* d_seg, int T,
+                    double min_det, long long* d_best_idx, double* d_best_quality, unsigned char* d_ready, void* stream);
 /* d_probes: [P][512] f32.  normalize != 0 applies q/(||q||+1e-8) first (search()).
  * Outputs (device): scores f32 [P][k], idx i64 [P][k] (global ids, -1 = fewer than k rows),
- * accept u8 [P] (top-1 score >= thr), scores64 f64 [P][k] (optional, for cross-rank merge). */
+ * accept u8 [P] (top-1 score >= thr), scores64 f64 [P][k] (optional, for cross-rank merge).
+ * Any k >= 1 (search() accepts any top_k, gallery_manager.py:197): k <= 32 on galleries of >= 4096 rows runs the
+ * tensor-core filter + exact re-score + proof, everything else the dense exact scan.
+ * Enqueue only: no host synchronisation, no device-to-host copy the caller has to wait for (CUDA-graph capturable
+ * once the workspaces exist, i.e. from the second call with the same P / k on). */
 int frb_match(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, int normalize,
               float* d_scores, long long* d_idx, unsigned char* d_accept, double* d_scores64, void* stream);
-/* how many probes of the last frb_match needed the exact re-scan (filter proof failed) */
+/* how many probes of the last frb_match needed the exact re-scan (filter proof failed); waits for that match */
 int frb_match_last_flagged(frb_ctx* ctx);
-/* merge G gathered per-rank top-k lists: in [G][P][k] -> out [P][k] */
+/* frb_match with the result as 16-byte records [P][k] = (f64 score, i64 global id): the payload ONE all-gather moves */
+int frb_match_packed(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, int normalize, void* d_records,
+                     void* stream);
+/* merge G gathered per-rank top-k lists: in [G][P][k] -> out [P][k] (canonical order: score desc, id asc) */
 int frb_topk_merge(frb_ctx* ctx, const double* d_in_scores64, const long long* d_in_idx, int G, int P, int k,
                    float thr, float* d_scores, long long* d_idx, unsigned char* d_accept, double* d_scores64,
                    void* stream);
+int frb_topk_merge_packed(frb_ctx* ctx, const void* d_records, int G, int P, int k, float thr, float* d_scores,
+                          long long* d_idx, unsigned char* d_accept, void* stream);
+
+/* ---- identity-sharded gallery over peer memory (NVLink P2P; new work, the reference is single-device) ----
+ * One process per GPU.  frb_xchg_create allocates this rank's exchange buffer (probes of all ranks, two parities of
+ * result slots, flag words) and returns its 64-byte cudaIpc handle; the caller all-gathers the handles (any transport:
+ * torch.distributed, files) and passes all of them to frb_xchg_connect.  world <= 8, max_k <= 32. */
+int frb_xchg_create(frb_ctx* ctx, int world, int rank, int max_probes, int max_k, void* h_handle_out64);
+int frb_xchg_connect(frb_ctx* ctx, const void* h_handles_all);
+/* 0, or 1 + the rank a device-side wait gave up on (FRB_XCHG_TIMEOUT_MS, default 20 s; the kernel then traps) */
+int frb_xchg_status(frb_ctx* ctx);
+/* Collective: every rank passes its own rows [p_lo, p_lo + p_cnt) of the P_total probes (d_local_probes [p_cnt][512]
+ * f32) and holds its shard (frb_gallery_upload with first_global_id = shard start).  Probes are stored into every
+ * rank's buffer by the prepare kernel, each rank matches ALL probes against its shard, every finished row's k records
+ * go straight into every rank's result slot from the finalize kernel, and a merge kernel that waits on the peers'
+ * flags writes the global top-k of ALL P_total probes on every rank.  No NCCL and no host synchronisation on the data
+ * path; results equal frb_match against the unsharded gallery bit for bit. */
+int frb_match_sharded(frb_ctx* ctx, const float* d_local_probes, int p_lo, int p_cnt, int P_total, int k, float thr,
+                      int normalize, float* d_scores, long long* d_idx, unsigned char* d_accept, void* stream);
 
 /* ---- host-buffer entry points (what the Python drop-in calls; copies happen inside) ---- */
 /* h_rgb: [B][S][S][3] u8 -> h_emb [B][512] f32 (+ h_norm [B] optional) */
@@ -170,6 +208,9 @@ int frb_embed_match_host(frb_ctx* ctx, const uint8_t* h_rgb, int B, int S, int f
                          float* h_emb, float* h_scores, long long* h_idx, unsigned char* h_accept);
 
 /* ---- test hooks (used by tests/ only) ---- */
+/* ranks living in one process (one ctx each) hand each other the raw exchange buffer instead of a cudaIpc handle */
+void* frb_xchg_local_buffer(frb_ctx* ctx);
+int frb_xchg_connect_local(frb_ctx* ctx, int peer_rank, void* d_peer_buffer);
 /* C[M][N] f32 = A[M][K] * B[N][K]^T, bf16 inputs, K % 64 == 0, N % 64 == 0 */
 int frb_debug_gemm(frb_ctx* ctx, const void* d_A, const void* d_B, int M, int N, int K, int splits,
                    float* d_C, void* stream);

@@ -1,6 +1,7 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU exchange logic in dist.py: shard bounds, the variable-length
-probe all-gather, the per-rank top-k all-gather and the merge — with the oracle as local matcher/merger
-(on GPUs the same exchange runs with frb_match / frb_topk_merge, see tests/test_gpu_dist.py)."""
+"""world_size-2 gloo tests (CPU) of the multi-GPU exchange logic in dist.py: shard bounds, the single padded
+probe all-gather (uneven split, no count exchange), the single all-gather of packed (f64 score, i64 id) records and
+the merge - with the oracle as local matcher/merger.  On GPUs the same exchange runs with frb_match_packed /
+frb_topk_merge_packed over NCCL and as frb_match_sharded over peer memory: tests/test_gpu_dist.py."""
 import os
 import socket
 
@@ -69,7 +70,10 @@ def _worker(rank, world, port, N, P, k, out):
     lo, hi = fd.shard_bounds(N, world, rank)
     sg.upload_shard(G[lo:hi], N)
     plo, phi = fd.split_probes(P, world, rank)    # uneven split: exercises the var-len gather
-    sc, ix, ac = sg.match(torch.from_numpy(probes[plo:phi]), k=k, thr=0.5)
+    assert sg.exchange == "nccl"             # injected matcher -> the collective path (gloo here)
+    sc, ix, ac = sg.match(torch.from_numpy(probes[plo:phi]), k=k, thr=0.5, n_probes=P)
+    every = fd.all_gather_balanced(torch.from_numpy(probes[plo:phi]), P)
+    assert torch.equal(every, torch.from_numpy(probes))
     eidx, esc = og.search_batch(G, probes, k)
     ok = bool(np.array_equal(ix.numpy(), eidx) and np.allclose(sc.numpy(), esc, atol=1e-6) and ix[0, 0].item() == 2
               and ix[0, 1].item() == N // 2 + 3 and ac[0].item() == 1)
@@ -85,3 +89,15 @@ def test_sharded_gallery_exchange_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), 1001, 7, 5, out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_pack_records_roundtrip():
+    sc = torch.tensor([[0.5, -float("inf")], [1.0 - 2 ** -52, 0.25]], dtype=torch.float64)
+    ix = torch.tensor([[7, -1], [1 << 40, 3]], dtype=torch.int64)
+    rec = fd.pack_records(sc, ix)
+    assert rec.shape == (2, 2, 2) and rec.dtype == torch.int64 and rec.is_contiguous()
+    s2, i2 = fd.unpack_records(rec)
+    assert torch.equal(s2, sc) and torch.equal(i2, ix)
+    # the record layout is the device's TopkRec: 8 bytes of f64 score, then 8 bytes of i64 id
+    raw = rec.numpy().tobytes()
+    assert np.frombuffer(raw[:8], np.float64)[0] == 0.5 and np.frombuffer(raw[8:16], np.int64)[0] == 7

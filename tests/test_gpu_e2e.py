@@ -78,7 +78,6 @@ def test_config4_warp_embed_match_stream(ctx):
     B, S = 1024, 112
     sd = ob.random_state_dict("ir_101", "adaface", seed=3)
     weights.build_program(sd, "ir_101", "adaface").load_into(ctx)
-    ctx.backbone_token = None
     tpl = similarity_template(S)
     frames = np.stack([cv2.GaussianBlur(rng.integers(0, 256, (256, 256, 3), dtype=np.uint8), (0, 0), 2.0) for _ in range(16)])
     jobs = (_native.WarpJob * B)()
@@ -115,7 +114,6 @@ def test_config4_warp_embed_match_stream(ctx):
     where = torch.randperm(N, generator=g, device=dev)[:B]
     G[where] = emb
     ctx.frb_gallery_upload(G.data_ptr(), N, 0, 1)
-    ctx.gallery_token = None
     sc = torch.empty((B, 5), dtype=torch.float32, device=dev)
     ix = torch.empty((B, 5), dtype=torch.int64, device=dev)
     ac = torch.empty((B,), dtype=torch.uint8, device=dev)

@@ -72,7 +72,6 @@ def test_device_matches_bf16_emulation(ctx):
     sd = ob.random_state_dict("ir_50", "adaface", seed=4)
     prog = weights.build_program(sd, "ir_50", "adaface", keep_debug=True)
     prog.load_into(ctx)
-    ctx.backbone_token = None
     crops = np.stack(_crops(np.random.default_rng(3), 6))
     emb = np.empty((6, 512), np.float32)
     nrm = np.empty((6,), np.float32)
@@ -104,7 +103,6 @@ def test_flip_fusion_config5(ctx):
     sd = ob.random_state_dict("ir_50", "iresnet", seed=21)
     prog = weights.build_program(sd, "ir_50", "iresnet")
     prog.load_into(ctx)
-    ctx.backbone_token = None
     crops = _crops(np.random.default_rng(22), 5)
     stack = np.stack(crops)
     got = np.empty((5, 512), np.float32)

@@ -250,3 +250,85 @@ def test_config5_10m_identity_gallery_sharded_equals_unsharded(ctx):
     ctx.frb_gallery_upload(G[:256].data_ptr(), 256, 0, 1)      # release the 10M-row copies held by the context
     del G
     torch.cuda.empty_cache()
+
+
+def test_flagged_rows_are_fixed_on_the_device(ctx):
+    """Rows whose filter proof fails are re-done by the exact fix-up kernels, which take the row list and its length
+    from the device (no D2H + synchronise inside frb_match).  200 identical copies of one row defeat the proof (the
+    64 re-scored survivors tie with everything the filter kept below them); with 150 such probes the fix-up walks
+    its list in several strides (16 rows in flight in the partial kernel, 64 in the merge kernel)."""
+    rng = np.random.default_rng(77)
+    N, P, k = 30000, 150, 5
+    G = _unit(rng.standard_normal((N, 512)))
+    dup = np.sort(rng.choice(N, 200, replace=False))
+    G[dup] = G[dup[0]]
+    probes = _unit(rng.standard_normal((P, 512)))
+    hit = np.arange(0, P, 1)[::1][:120]
+    probes[hit] = _unit(G[dup[0]][None] + 0.02 * rng.standard_normal((len(hit), 512)))
+    sc, ix, ac = _match(ctx, G, probes, k, thr=0.4)
+    flagged = ctx._lib.frb_match_last_flagged(ctx.handle)
+    assert flagged >= len(hit), flagged
+    assert (ix[hit] == dup[:k][None]).all()            # exact ties: the lowest ids win
+    _check(G, probes, k, sc, ix, ac, 0.4)
+
+
+@pytest.mark.parametrize("N,k", [(500, 50), (20000, 33), (20000, 100)])
+def test_top_k_above_32(ctx, N, k):
+    """search() accepts any top_k (gallery_manager.py:197); k > 32 takes the dense exact scan."""
+    rng = np.random.default_rng(N + k)
+    G = _unit(rng.standard_normal((N, 512)))
+    probes = _unit(rng.standard_normal((7, 512)))
+    probes[0] = G[5]
+    sc, ix, ac = _match(ctx, G, probes, k, thr=0.4)
+    _check(G, probes, k, sc, ix, ac, 0.4)
+
+
+def test_gallery_manager_search_any_top_k(ctx, tmp_path):
+    from facerecognitionpipeline_b200.gallery_manager import GalleryManager
+    rng = np.random.default_rng(5)
+    gm = GalleryManager(gallery_path=str(tmp_path / "g.pkl"))
+    E = _unit(rng.standard_normal((40, 512)))
+    for i in range(40):
+        gm.add_student(f"STU{i:04d}", f"n{i}", E[i:i + 1])
+    res = gm.search(E[7], top_k=100)                    # more than the gallery holds: min(top_k, N) rows, as numpy slicing
+    assert len(res) == 40 and res[0][0] == "STU0007"
+    s = np.dot(E, E[7] / (np.linalg.norm(E[7]) + 1e-8))
+    order = np.lexsort((np.arange(40), -s))
+    assert [r[0] for r in res] == [f"STU{i:04d}" for i in order]
+    assert len(gm.search(E[7], top_k=35)) == 35
+
+
+def test_match_enqueues_without_synchronising_and_is_graph_capturable(ctx):
+    """frb_match only enqueues (the per-call D2H + cudaStreamSynchronize is gone): once its workspaces
+    exist the whole call can be captured into a CUDA graph and replayed on new probe contents."""
+    import torch
+    rng = np.random.default_rng(31)
+    N, P, k = 20000, 96, 5
+    G = _unit(rng.standard_normal((N, 512)))
+    dev = torch.device("cuda", 0)
+    ctx.frb_gallery_upload(G.ctypes.data, N, 0, 0)
+    pr = torch.empty((P, 512), dtype=torch.float32, device=dev)
+    s32 = torch.empty((P, k), dtype=torch.float32, device=dev)
+    ix = torch.empty((P, k), dtype=torch.int64, device=dev)
+    ac = torch.empty((P,), dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream(dev)
+
+    def enqueue(stream):
+        ctx.frb_match(pr.data_ptr(), P, k, 0.4, 1, s32.data_ptr(), ix.data_ptr(), ac.data_ptr(), None,
+                      C.c_void_p(stream.cuda_stream))
+
+    probes0 = _unit(rng.standard_normal((P, 512)))
+    pr.copy_(torch.from_numpy(probes0))
+    with torch.cuda.stream(side):
+        enqueue(side)                                   # warm-up: allocates the workspaces
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        enqueue(side)
+    for seed in (1, 2):
+        probes = _unit(G[np.random.default_rng(seed).integers(0, N, P)] + 0.05 * np.random.default_rng(seed).standard_normal((P, 512)))
+        pr.copy_(torch.from_numpy(probes))
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        _check(G, probes, k, s32.cpu().numpy(), ix.cpu().numpy(), ac.cpu().numpy(), 0.4)
