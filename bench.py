@@ -197,6 +197,8 @@ def run_reference(args):
               f"{gallery_rows} x 512 f32 (matrix cached); faces/s = 1 / (embed s/face + match s/probe)")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec_per_face * 1e3 * n_faces, higher_is_better=True, scaling="weak", vs_baseline=None,
+                ms_per_step_note=f"extrapolated: {n_faces} x (embed s/face + match s/probe); a step actually times {n_faces} faces "
+                                 f"embedded but only {n_probes} probes matched (bounded sample of the same workload)",
                 dtype="f32", data="synthetic", impl="reference",
                 config=dict(workload=f"IR-101 embed + top-5 match vs {gallery_rows}-identity gallery, CPU reference path",
                             batch_per_gpu=n_faces, gallery_rows=gallery_rows),
@@ -235,7 +237,8 @@ def run_ours(args):
         blk = torch.randn((min(1 << 18, N - s0), 512), generator=g, device=dev)
         G[s0:s0 + blk.shape[0]] = blk / blk.norm(dim=1, keepdim=True)
     ctx.frb_gallery_upload(G.data_ptr(), N, 0, 1)
-    del G
+    if world == 1:
+        del G          # (world > 1: the identity-sharded section below re-uploads this rank's rows of the same gallery)
 
     # inputs: NBUF distinct crop batches (rotated so no step re-reads a warm input)
     NBUF = 16
@@ -325,11 +328,132 @@ def run_ours(args):
     h2d = B * 112 * 112 * 3
     d2h = B * topk * 4 + B * topk * 8 + B
 
+    peaks = load_peaks()
+
+    def timed(fn, reps, warm=3):
+        """CUDA-event time per call (ms) on the launch stream, barrier on both sides, max over ranks."""
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        b.synchronize()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / reps)
+
+    # ---- BASELINE configs[2]: 4096 probes x N gallery, top-5.  One GPU: the whole gallery; N GPUs: sharded by identity,
+    # probes split across the ranks, exchange + merge inside the timed region (dist.ShardedGallery).
+    P3 = 4096
+    g3 = torch.Generator(device=dev).manual_seed(77)          # same seed on every rank: the same probe set everywhere
+    probes3 = torch.randn((P3, 512), generator=g3, device=dev)
+    sc3 = torch.empty((P3, topk), dtype=torch.float32, device=dev)
+    ix3 = torch.empty((P3, topk), dtype=torch.int64, device=dev)
+    ac3 = torch.empty((P3,), dtype=torch.uint8, device=dev)
+
+    def match_all():
+        ctx.frb_match(probes3.data_ptr(), P3, topk, thr, 1, sc3.data_ptr(), ix3.data_ptr(), ac3.data_ptr(), None, st)
+
+    c3_1gpu_ms = timed(match_all, 10)
+    ms3 = (C.c_float * 3)()
+    c3_parts = []
+    for _ in range(3):
+        ctx.frb_match_profile(probes3.data_ptr(), P3, topk, thr, 1, sc3.data_ptr(), ix3.data_ptr(), ac3.data_ptr(), st, ms3)
+        c3_parts.append(list(ms3))
+    c3_parts = np.median(np.array(c3_parts), axis=0)
+    p256_parts = []
+    for i in range(4):
+        ctx.frb_match_profile(emb.data_ptr(), B, topk, thr, 1, sc.data_ptr(), ix.data_ptr(), ac.data_ptr(), st, ms3)
+        p256_parts.append(list(ms3))
+    p256_parts = np.median(np.array(p256_parts[1:]), axis=0)
+    sharded = None
+    if world > 1:
+        from facerecognitionpipeline_b200.dist import ShardedGallery, shard_bounds, split_probes
+        match_all()
+        torch.cuda.synchronize(dev)
+        ix_ref = ix3.clone()
+        ac_ref = ac3.clone()
+        lo, hi = shard_bounds(N, world, rank)
+        plo, phi = split_probes(P3, world, rank)
+        mine = probes3[plo:phi].contiguous()
+        res = {}
+        sg_peer = None
+        for mode in ("peer", "nccl"):
+            try:
+                sg = ShardedGallery(ctx=ctx, exchange=mode, max_probes=P3, max_k=8)
+            except RuntimeError as e:          # no peer access between the GPUs: the NCCL exchange still runs
+                res[mode] = dict(error=str(e)[:200])
+                continue
+            if mode == "peer":
+                sg_peer = sg
+            sg.upload_shard(G[lo:hi], N)
+            o_sc, o_ix, o_ac = sg.match(mine, k=topk, thr=thr, n_probes=P3)
+            torch.cuda.synchronize(dev)
+            same = bool(torch.equal(o_ix, ix_ref) and torch.equal(o_ac, ac_ref))
+            flag = torch.tensor([int(same)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ms = timed(lambda: sg.match(mine, k=topk, thr=thr, n_probes=P3), 20)
+            res[mode] = dict(ms=ms, ids_identical_to_unsharded=bool(flag.item()))
+        best = min((m for m in res if "ms" in res[m]), key=lambda m: res[m]["ms"])
+        sharded = dict(workload=f"{P3} probes x {N} x 512 gallery, top-{topk}, gallery sharded by identity over {world} GPUs, "
+                                f"probes split over the ranks; probe exchange + per-shard match + top-k exchange + merge timed",
+                       exchange=best, sharded_match_ms=res[best]["ms"], sharded_probes_per_s=P3 / (res[best]["ms"] / 1e3),
+                       one_gpu_match_ms=c3_1gpu_ms, sharded_vs_1gpu=c3_1gpu_ms / res[best]["ms"],
+                       strong_scaling_efficiency=c3_1gpu_ms / res[best]["ms"] / world,
+                       tflops=P3 * 1024.0 * N / (res[best]["ms"] / 1e3) / 1e12, by_exchange=res)
+        del G
+        # back to the replicated gallery is not needed: everything below works on the embed path only
+
+    # ---- BASELINE configs[3]: landmark warp -> IR-101 -> match at batch 1024 per GPU (data-parallel).  The match runs
+    # against the gallery resident now (whole gallery at 1 GPU; this rank's shard after the sharded section).
+    c4 = None
+    if not args.no_c4:
+        import cv2
+        from facerecognitionpipeline_b200.face_recognition import estimate_matrix, similarity_template
+        B4 = 1024
+        r4 = np.random.default_rng(7 + rank)
+        tpl = similarity_template(112)
+        frames = np.stack([cv2.GaussianBlur(r4.integers(0, 256, (256, 256, 3), dtype=np.uint8), (0, 0), 2.0) for _ in range(16)])
+        jobs = (_native.WarpJob * B4)()
+        src_bytes = 0.0
+        for i in range(B4):
+            ang, scl = np.deg2rad(r4.uniform(-20, 20)), r4.uniform(1.5, 2.2)
+            R = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]]) * scl
+            lm = ((tpl - 56) @ R.T + np.array([128 + r4.uniform(-8, 8), 128 + r4.uniform(-8, 8)]) + r4.normal(0, 0.5, (5, 2))).astype(np.float32)
+            M = estimate_matrix(lm, tpl)
+            jobs[i].src_off, jobs[i].H, jobs[i].W, jobs[i].pitch = (i % 16) * 256 * 256 * 3, 256, 256, 256 * 3
+            for j, v in enumerate(np.asarray(M, np.float64).reshape(6)):
+                jobs[i].M[j] = float(v)
+            src_bytes += (112 * scl) ** 2 * 3
+        d_frames = torch.from_numpy(frames).to(dev)
+        x4 = torch.empty((B4, 112, 112, 3), dtype=torch.bfloat16, device=dev)
+        emb4 = torch.empty((B4, 512), dtype=torch.float32, device=dev)
+        sc4 = torch.empty((B4, topk), dtype=torch.float32, device=dev)
+        ix4 = torch.empty((B4, topk), dtype=torch.int64, device=dev)
+        ac4 = torch.empty((B4,), dtype=torch.uint8, device=dev)
+
+        def c4_step():
+            ctx.frb_warp_normalize(d_frames.data_ptr(), jobs, B4, 112, None, x4.data_ptr(), st)
+            ctx.frb_embed(x4.data_ptr(), B4, flags, emb4.data_ptr(), None, None, st)
+            ctx.frb_match(emb4.data_ptr(), B4, topk, thr, 1, sc4.data_ptr(), ix4.data_ptr(), ac4.data_ptr(), None, st)
+
+        c4_ms = timed(c4_step, 5)
+        warp_ms = timed(lambda: ctx.frb_warp_normalize(d_frames.data_ptr(), jobs, B4, 112, None, x4.data_ptr(), st), 10)
+        warp_bytes = src_bytes + B4 * 75264.0
+        c4 = dict(workload=f"BASELINE configs[3]: 5-landmark warp+normalise -> IR-101 -> top-{topk} match, batch {B4} per GPU, "
+                           f"probe-dp{world}; warp sources 256x256 RGB frames resident in HBM, matrices from cv2.estimateAffinePartial2D on the host (untimed)",
+                  faces_per_s=world * B4 / (c4_ms / 1e3), ms_per_step=c4_ms, batch_per_gpu=B4,
+                  backbone_frac_of_burst=(flops_face * B4 / (c4_ms / 1e3) / 1e12) / peaks["tf_burst"],
+                  warp=dict(ms=warp_ms, algorithmic_bytes=warp_bytes, gbs=warp_bytes / (warp_ms / 1e3) / 1e9,
+                            frac_of_hbm=warp_bytes / (warp_ms / 1e3) / 1e9 / peaks["hbm"]))
+        del x4, emb4
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = load_peaks()
     # ---- roofline of the dominant kernel: per-layer CUDA-event durations of a few extra (untimed) steps through
     # frb_embed_profile; the kernel with the largest share of the embed section is reported (ALGORITHMIC flops of
     # its launches / their summed duration).  Event-separated launches do not overlap, so this is per-launch time.
@@ -370,6 +494,40 @@ def run_ours(args):
                          f"{PROF_STEPS} steps after the timed region); peak = bf16_tflops_sustained ({peaks['src']}). "
                          f"backbone_section = whole IR-101 embed ({flops_face / 1e9:.3f} GFLOP/face x {B} / {embed_ms:.3f} ms "
                          f"inside the timed steps, programmatic dependent launch on); match section {match_ms:.3f} ms/step")
+    # every kernel of the step against ITS roofline (burst and sustained tensor peak, or the measured copy bandwidth)
+    def tensor_entry(name, gflop, us, n):
+        tf = gflop / 1e3 / (us / 1e6)
+        return dict(kernel=name, bound="tensor", launches_per_step=n, us_per_step=us, algorithmic_gflop=gflop, achieved=tf,
+                    unit="TFLOP/s", frac_of_burst=tf / peaks["tf_burst"], frac_of_sustained=tf / peaks["tf_sustained"])
+
+    def hbm_entry(name, nbytes, us, n, note=None):
+        gbs = nbytes / 1e9 / (us / 1e6)
+        d = dict(kernel=name, bound="hbm", launches_per_step=n, us_per_step=us, algorithmic_bytes=nbytes, achieved=gbs,
+                 unit="GB/s", frac_of_hbm=gbs / peaks["hbm"])
+        if note:
+            d["note"] = note
+        return d
+
+    per_kernel_list = []
+    for kid_, (n_, ms_, fl_) in sorted(per_kernel.items()):
+        us = ms_ / PROF_STEPS * 1e3
+        if kid_ == 0:      # stem: reads the bf16 crops, writes the 112x112x64 activation
+            per_kernel_list.append(hbm_entry(KNAMES[0], B * (112 * 112 * 3 * 2 + 112 * 112 * 64 * 2.0), us, n_ // PROF_STEPS,
+                                             f"also {fl_ / PROF_STEPS / 1e9:.1f} GFLOP on the tensor cores (K = 27 padded to 32)"))
+        else:
+            per_kernel_list.append(tensor_entry(KNAMES[kid_], fl_ / PROF_STEPS / 1e9, us, n_ // PROF_STEPS))
+    per_kernel_list.append(hbm_entry("match_filter2_kernel (P = %d)" % B, N * 1024.0, float(p256_parts[1]) * 1e3, 1,
+                                     "HBM-bound at this probe count: the bf16 gallery is streamed once"))
+    per_kernel_list.append(dict(kernel="probe_prepare_kernel", us_per_step=float(p256_parts[0]) * 1e3, bound="latency"))
+    per_kernel_list.append(dict(kernel="match_finalize_kernel + exact fix-up kernels (device-side row list)",
+                                us_per_step=float(p256_parts[2]) * 1e3, bound="latency"))
+    per_kernel_list.append(tensor_entry("match_filter2_kernel (P = 4096, BASELINE configs[2] on one GPU)",
+                                        P3 * 1024.0 * N / 1e9, float(c3_parts[1]) * 1e3, 1))
+    if c4:
+        per_kernel_list.append(hbm_entry("warp_normalize_kernel (1024 faces)", c4["warp"]["algorithmic_bytes"],
+                                         c4["warp"]["ms"] * 1e3, 1, "source footprint + 75 264 B written per face (SURVEY 8d)"))
+    roofline["frac_of_burst"] = dom_tf / peaks["tf_burst"]
+    roofline["per_kernel"] = per_kernel_list
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         ref = CpuReference(N)
@@ -391,7 +549,18 @@ def run_ours(args):
                                f"activations) exceeds the 126 MB L2; input crops rotate over {NBUF} distinct batches"),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                gpu_launches=int(launches), roofline=roofline, embed_ms=embed_ms, match_ms=match_ms)
+                gpu_launches=int(launches), roofline=roofline, embed_ms=embed_ms, match_ms=match_ms,
+                match_4096=dict(workload=f"BASELINE configs[2] on ONE GPU: {P3} probes x {N} x 512, top-{topk}", ms=c3_1gpu_ms,
+                                probes_per_s=P3 / (c3_1gpu_ms / 1e3), tflops=P3 * 1024.0 * N / (c3_1gpu_ms / 1e3) / 1e12,
+                                frac_of_burst=P3 * 1024.0 * N / (c3_1gpu_ms / 1e3) / 1e12 / peaks["tf_burst"],
+                                parts_ms=dict(prepare=float(c3_parts[0]), filter=float(c3_parts[1]), finalize=float(c3_parts[2]))))
+    if sharded:
+        line["sharded"] = sharded
+        line["sharded_match_ms"] = sharded["sharded_match_ms"]
+        line["sharded_probes_per_s"] = sharded["sharded_probes_per_s"]
+        line["sharded_vs_1gpu"] = sharded["sharded_vs_1gpu"]
+    if c4:
+        line["c4"] = c4
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -408,6 +577,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--gallery", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the warp -> embed -> match batch-1024 sub-measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

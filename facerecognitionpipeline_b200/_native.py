@@ -85,6 +85,7 @@ SIGNATURES = {
     "frb_track_consensus": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, C.c_double, _i, C.c_double, _vp, _vp]),
     "frb_best_frames": (_i, [_vp, _vp, _vp, _vp, _i, C.c_double, _vp, _vp, _vp, _vp]),
     "frb_match": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "frb_match_profile": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "frb_match_last_flagged": (_i, [_vp]),
     "frb_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "frb_topk_merge_packed": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),

@@ -139,6 +139,8 @@ struct frb_ctx {
   bool flag_event_pending = false;
   TopkRec* d_exact_part = nullptr; size_t exact_part_cap = 0;
   TopkRec* d_merge_rec = nullptr; size_t merge_rec_cap = 0;
+  cudaEvent_t match_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // frb_match_profile: prepare | filter | finalize + fix-up
+  bool match_profiling = false;
   // generations: bumped by every upload, so a wrapper can tell whether what it uploaded is still resident
   long long gallery_gen = 0, backbone_gen = 0;
   // the workspaces above are shared by every call on this ctx: a call on another stream than the previous one first
@@ -803,6 +805,7 @@ extern "C" void frb_ctx_destroy(frb_ctx* ctx) {
   if (ctx->flag_event) cudaEventDestroy(ctx->flag_event);
   if (ctx->ws_event) cudaEventDestroy(ctx->ws_event);
   for (auto e : ctx->prof_events) cudaEventDestroy(e);
+  for (auto e : ctx->match_prof_ev) if (e) cudaEventDestroy(e);
   for (auto* b : ctx->d_bufs)
     if (b) cudaFree(b);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1622,6 +1625,7 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
   mp.cand_idx = ctx->d_cand_idx;
   CUtensorMap tmP;
   if (make_tmap_2d(ctx, &tmP, d_probe_bf16, 512, static_cast<uint64_t>(P), 128)) return 1;
+  if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[1], st));
   if (pair_mode) {
     if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_filter2_kernel), Match2Smem::kTotal)) return 1;
     cudaLaunchConfig_t cfg = {};
@@ -1641,6 +1645,7 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
   }
   CK(cudaGetLastError());
   ctx->launches++;
+  if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[2], st));
   FinalizeParams fp;
   fp.cand_score = ctx->d_cand_score; fp.cand_idx = ctx->d_cand_idx; fp.slices = mp.slices;
   fp.probes = d_probe_f32; fp.gallery = ctx->d_gal; fp.N = N; fp.first_global_id = ctx->gal_first;
@@ -1664,6 +1669,7 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
   match_exact_fix_kernel<<<std::min(P, 64), 128, 0, st>>>(xp, kExactBlocks);
   CK(cudaGetLastError());
   ctx->launches++;
+  if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[3], st));
   // frb_match_last_flagged: the count travels to pinned memory behind an event, read only when somebody asks
   CK(cudaMemcpyAsync(ctx->h_flag_count, ctx->d_match_ctr, 4, cudaMemcpyDeviceToHost, st));
   if (stream_capturing(st)) {   // inside a graph: the count still lands in pinned memory on every replay
@@ -1688,6 +1694,7 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
   if (match_workspace(ctx, P)) return 1;
   double* s64 = d_scores64;
   if (!s64 && scores64_scratch(ctx, static_cast<size_t>(P) * k, &s64)) return 1;
+  if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[0], st));
   probe_prepare_kernel<<<P, 128, 0, st>>>(d_probes, normalize, ctx->d_probe_f32, ctx->d_probe_bf16);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -1695,6 +1702,29 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
 }
 
 }  // namespace
+
+// Measurement aid (bench.py per-kernel roofline): frb_match with CUDA events between its three parts; h_ms3 = prepare,
+// filter kernel, finalize + exact fix-up (ms).  Needs the tensor-core path (N >= 4096, k <= 32); synchronises.
+extern "C" int frb_match_profile(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, int normalize,
+                                 float* d_scores, long long* d_idx, unsigned char* d_accept, void* stream, float* h_ms3) {
+  if (!ctx) return 1;
+  if (P <= 0 || !h_ms3) return fail(ctx, "frb_match_profile: bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->gal_N < kExactOnlyBelow || k > kExactMaxK) return fail(ctx, "frb_match_profile: needs the tensor-core path");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (auto& e : ctx->match_prof_ev)
+    if (!e) CK(cudaEventCreate(&e));
+  if (ws_begin(ctx, st)) return 1;
+  ctx->match_profiling = true;
+  const int rc = match_locked(ctx, d_probes, P, k, thr, normalize, d_scores, d_idx, d_accept, nullptr, st);
+  ctx->match_profiling = false;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(st));
+  ctx->ws_valid = false;
+  for (int i = 0; i < 3; ++i) CK(cudaEventElapsedTime(&h_ms3[i], ctx->match_prof_ev[i], ctx->match_prof_ev[i + 1]));
+  return 0;
+}
 
 // d_probes: [P][512] f32.  Any k >= 1: k <= 32 takes the tensor-core filter + exact re-score + proof (galleries of
 // >= 4096 rows), larger k or smaller galleries the dense exact scan (search() accepts any top_k, gallery_manager.py:197).

@@ -10,9 +10,9 @@ Differences that are visible and intended:
     no checkpoint files are shipped with the reference either, .gitignore:15,18,33).
   * `batch_size` in `extract_embeddings_batch` is accepted but the device path chunks by
     `self.max_batch` (eval-mode results do not depend on the chunking).
-  * ArcFace: the reference loads an ONNX export of insightface iresnet via onnxruntime
-    (face_embedder.py:64-88).  Here the same architecture runs from an iresnet-layout torch state
-    dict (`.pth`); an `.onnx` path raises NotImplementedError (no ONNX parser in this build).
+  * ArcFace: the reference runs an ONNX export of insightface iresnet through onnxruntime
+    (face_embedder.py:64-88).  Here the `.onnx` file's initializers are read directly (`onnx_import`, no onnx /
+    onnxruntime package) and mapped onto the same device program an iresnet `.pth` state dict builds.
 """
 from __future__ import annotations
 
@@ -79,11 +79,16 @@ class FaceEmbedder:
                 model_path = table[architecture]
             if not os.path.exists(model_path):
                 raise FileNotFoundError(f"Model file not found at: {model_path}")
-            if str(model_path).endswith(".onnx"):
-                raise NotImplementedError(
-                    "ONNX import is not available in this build; pass the insightface iresnet state dict (.pth)")
             print(f"Loading {model_type} model ({architecture}) from {model_path}...")
-            state_dict = weights.load_checkpoint_state_dict(model_path)
+            if str(model_path).lower().endswith(".onnx"):
+                from . import onnx_import
+                if layout != "iresnet":
+                    raise ValueError("an .onnx model file holds the ArcFace (insightface iresnet) export: use model_type='arcface'")
+                state_dict, found = onnx_import.onnx_to_iresnet_state_dict(model_path)
+                if found != architecture:
+                    raise ValueError(f"{model_path} holds an {found} backbone, architecture={architecture!r} was requested")
+            else:
+                state_dict = weights.load_checkpoint_state_dict(model_path)
         self._program = weights.build_program(state_dict, architecture, layout)
         self._ctx = _native.default_context(index)
         with self._ctx.lock:
@@ -91,7 +96,7 @@ class FaceEmbedder:
             self._loaded_gen = self._ctx.backbone_generation()
         self._flags = _native.FRB_EMBED_L2 if layout == "adaface" else 0
         self.input_size = (112, 112)
-        self.is_onnx = False
+        self.is_onnx = str(model_path or "").lower().endswith(".onnx")   # informational, as the reference's attribute
         self.model = self  # the reference exposes `.model`; here the embedder is the model handle
         print(f"{model_type} model loaded on {self.device} (libfrb200, sm_100a)")
 

@@ -163,6 +163,10 @@ int frb_best_frames(frb_ctx* ctx, const double* d_det, const double* d_blur, con
  * once the workspaces exist, i.e. from the second call with the same P / k on). */
 int frb_match(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, int normalize,
               float* d_scores, long long* d_idx, unsigned char* d_accept, double* d_scores64, void* stream);
+/* measurement aid (bench.py per-kernel roofline): frb_match with CUDA events between prepare | filter kernel |
+ * finalize + exact fix-up; h_ms3 receives the three durations (ms).  Synchronises. */
+int frb_match_profile(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, int normalize, float* d_scores,
+                      long long* d_idx, unsigned char* d_accept, void* stream, float* h_ms3);
 /* how many probes of the last frb_match needed the exact re-scan (filter proof failed); waits for that match */
 int frb_match_last_flagged(frb_ctx* ctx);
 /* frb_match with the result as 16-byte records [P][k] = (f64 score, i64 global id): the payload ONE all-gather moves */
