@@ -1996,6 +1996,19 @@ extern "C" int frb_xchg_create(frb_ctx* ctx, int world, int rank, int max_probes
       ctx->match_cap_slices = slices;
     }
   }
+  // ... and every kernel of the sharded path is loaded now: with lazy module loading the FIRST launch of a kernel may
+  // synchronise the context - behind this rank's own wait kernel, which spins until a peer arrives
+  {
+    cudaFuncAttributes fa;
+    const void* kernels[] = {reinterpret_cast<const void*>(probe_push_kernel), reinterpret_cast<const void*>(probe_push_empty_kernel),
+                             reinterpret_cast<const void*>(xchg_wait_kernel), reinterpret_cast<const void*>(match_filter_kernel),
+                             reinterpret_cast<const void*>(match_filter2_kernel), reinterpret_cast<const void*>(match_finalize_kernel),
+                             reinterpret_cast<const void*>(match_exact_part_kernel), reinterpret_cast<const void*>(match_exact_fix_kernel),
+                             reinterpret_cast<const void*>(match_exact_scores_kernel), reinterpret_cast<const void*>(match_exact_topk_kernel),
+                             reinterpret_cast<const void*>(match_fill_empty_kernel), reinterpret_cast<const void*>(xchg_push_rows_kernel),
+                             reinterpret_cast<const void*>(topk_merge_kernel)};
+    for (const void* k : kernels) CK(cudaFuncGetAttributes(&fa, k));
+  }
   // opt the kernels into their shared-memory sizes now as well
   if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_filter2_kernel), Match2Smem::kTotal)) return 1;
   if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_filter_kernel), MatchSmem::kTotal)) return 1;

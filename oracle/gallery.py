@@ -48,10 +48,15 @@ def search_batch(gallery: np.ndarray, queries: np.ndarray, top_k: int = 5, norma
             # candidates by partition, then canonical order (score desc, index asc)
             cand = np.argpartition(-s, min(kk + 8, N - 1))[:min(kk + 9, N)] if N > kk + 16 else np.arange(N)
             thr = np.sort(s[cand])[::-1][kk - 1]
-            cand = np.nonzero(s >= thr)[0]
-            order = cand[np.lexsort((cand, -s[cand]))][:kk]
-            idx[s0 + r, :kk] = order
-            sc[s0 + r, :kk] = s[order]
+            # BLAS may round the dot product of IDENTICAL gallery rows differently depending on where the row sits in
+            # its blocking (seen at N = 7: 1 ulp between two copies of one row), which would break an exact tie the
+            # wrong way.  The candidates near the cut are therefore re-scored row by row with numpy's own pairwise
+            # sum (the same arithmetic `search` uses: position independent), and ordered on those scores.
+            cand = np.nonzero(s >= thr - 1e-9)[0]
+            exact = (G[cand] * q[s0 + r].astype(np.float64)[None, :]).sum(axis=1)
+            pick = np.lexsort((cand, -exact))[:kk]
+            idx[s0 + r, :kk] = cand[pick]
+            sc[s0 + r, :kk] = exact[pick]
     return idx, sc
 
 

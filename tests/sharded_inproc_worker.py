@@ -2,8 +2,10 @@
 
 Several ranks of an identity-sharded match live in this one process on one GPU: one ctx + one stream per rank, the
 exchange buffers handed over as raw pointers (frb_xchg_connect_local).  The ranks wait for each other ON THE DEVICE,
-so their kernels must really run concurrently: the parent sets CUDA_DEVICE_MAX_CONNECTIONS=32 (streams that alias onto
-one hardware queue would serialise a rank behind another rank's wait kernel) and a short FRB_XCHG_TIMEOUT_MS; a
+so their kernels must really run concurrently and no enqueue may synchronise the context: the parent sets
+CUDA_DEVICE_MAX_CONNECTIONS=32 (streams that alias onto one hardware queue would serialise a rank behind another rank's
+wait kernel), CUDA_MODULE_LOADING=EAGER (a lazily loaded kernel's first launch synchronises the context; frb_xchg_create
+also loads the kernels of the sharded path itself) and a short FRB_XCHG_TIMEOUT_MS; a
 device-side timeout traps and kills only this subprocess.  Prints one JSON line: {"ok": bool, "cases": [...]}."""
 import ctypes as C
 import json
@@ -94,6 +96,7 @@ def main():
     report, all_ok = [], True
     worlds = {}
     for world, N, P, k, dup in cases:
+        print(f"case world={world} N={N} P={P} k={k} dup={dup}", file=sys.stderr, flush=True)
         ranks = worlds.get(world) or worlds.setdefault(world, make_world(world))
         G, probes = problem(N + P, N, P, dup)
         thr, ok = 0.4, True
@@ -102,10 +105,16 @@ def main():
             if rep == 2:
                 probes = probes[::-1].copy()
                 eidx, esc, eacc = expect(G, probes, k, thr)
-            for sc, ix, ac in sharded_once(ranks, G, probes, k, thr):
+            for ri, (sc, ix, ac) in enumerate(sharded_once(ranks, G, probes, k, thr)):
                 fin = np.isfinite(esc)
-                ok = ok and np.array_equal(ix, eidx) and bool(np.abs(sc[fin] - esc[fin]).max() <= 1e-6) \
+                good = np.array_equal(ix, eidx) and bool(np.abs(sc[fin] - esc[fin]).max() <= 1e-6) \
                     and np.array_equal(ac.astype(bool), eacc)
+                if not good and ok:        # first mismatch of the case: say what differs
+                    bad = np.nonzero((ix != eidx).any(1))[0][:4]
+                    print(f"  MISMATCH rep {rep} rank {ri}: rows {bad.tolist()} got {ix[bad].tolist()} want {eidx[bad].tolist()} "
+                          f"scores {sc[bad].tolist()} want {esc[bad].tolist()} acc {ac[:8].tolist()} want {eacc[:8].astype(int).tolist()}",
+                          file=sys.stderr, flush=True)
+                ok = ok and good
         ok = ok and all(r.ctx.frb_xchg_status() == 0 for r in ranks)
         report.append(dict(case=[world, N, P, k, dup], ok=bool(ok)))
         all_ok = all_ok and ok

@@ -55,7 +55,7 @@ def test_sharded_match_in_process_world():
     import json
     import subprocess
     import sys
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", FRB_XCHG_TIMEOUT_MS="8000")
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER", FRB_XCHG_TIMEOUT_MS="8000")
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sharded_inproc_worker.py")
     proc = subprocess.run([sys.executable, worker, json.dumps(CASES)], env=env, capture_output=True, text=True, timeout=540)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
