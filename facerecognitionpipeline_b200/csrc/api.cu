@@ -79,6 +79,7 @@ struct frb_ctx {
   int conv_quad = 0;  // FRB_QUAD: gemm2_sm100_kernel<., 4> for Cout >= 256 (1) / >= 128 (2) layers
   int quad_clusters = 0;
   int use_slab = 1;   // activation-slab kernel for eligible 3x3 stride-1 layers (FRB_SLAB=0 disables)
+  int embed_chunk = 256;  // faces per pass of the layer program (FRB_EMBED_CHUNK; 0 = whole batch in one pass)
   int use_pdl = 1;    // programmatic dependent launch between backbone kernels (FRB_PDL=0 disables)
   int match_pair = 1;   // CTA-pair match filter for P > 128 (FRB_MATCH_PAIR=0 disables)
   int use_dataflow = 0;  // per-image progress counters instead of whole-grid dependencies (FRB_DATAFLOW=0 disables; needs PDL)
@@ -182,6 +183,9 @@ struct frb_ctx {
   std::vector<int> h_boxes;      // per-face source boxes of the last frb_warp_normalize call
   int slab_min_w = 0;            // FRB_SLAB_MINW=56: 28-pixel layers use the im2col pair kernel instead of the slab kernel
   int match_prefetch = 0;        // FRB_MATCH_PREFETCH=n: L2-prefetch gallery tiles n ahead of the TMA ring (pair kernel)
+  int warp_band = 0;             // FRB_WARP_BAND=1: band-staged kernel (every band's source spans copied to shared memory with
+                                 // 16-byte loads first; bit-identical).  MEASURED 3x SLOWER than the direct gather (2.28 vs 0.75 ms for
+                                 // 8192 faces, profiles/r02_summary.md): six block-wide phases per 2016 pixels at 4 blocks per SM.
   int warp_staged = 0;           // FRB_WARP_STAGED=1: stage each face's source box in shared memory first (bit-identical;
                                  // measured SLOWER, 1.14 vs 0.75 ms for 8192 faces: one 200 KB block per SM serialises
                                  // load and gather).  Default: the global-memory gather.
@@ -283,6 +287,34 @@ void fill_launch_attrs(cudaLaunchAttribute* attr, int cluster) {
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
+}
+
+// launch with programmatic stream serialization (the kernel calls pdl_wait() before it touches its predecessor's output)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, int cluster,
+                       Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 template <int BN, int MODE, int CL>
@@ -720,10 +752,12 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_MULTI_COOP")) ctx->multi_coop = atoi(e);
   if (const char* e = getenv("FRB_SLAB_MULTI")) ctx->slab_multi = atoi(e);
   if (const char* e = getenv("FRB_WARP_STAGED")) ctx->warp_staged = atoi(e);
+  if (const char* e = getenv("FRB_WARP_BAND")) ctx->warp_band = atoi(e);
   if (const char* e = getenv("FRB_MATCH_PREFETCH")) ctx->match_prefetch = atoi(e);
   if (const char* e = getenv("FRB_SLAB_MINW")) ctx->slab_min_w = atoi(e);
   if (const char* e = getenv("FRB_TAIL_SPLIT")) ctx->tail_split = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
+  if (const char* e = getenv("FRB_EMBED_CHUNK")) ctx->embed_chunk = atoi(e);
   if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
   if (const char* e = getenv("FRB_MATCH_PAIR")) ctx->match_pair = atoi(e);
   if (!ctx->use_pdl) ctx->use_dataflow = 0;
@@ -898,6 +932,22 @@ extern "C" int frb_warp_normalize(frb_ctx* ctx, const void* d_src_base, const fr
       ctx->launches++;
       return ws_end(ctx, st);
     }
+  }
+  if (ctx->warp_band) {   // experiment: every band's source spans staged in shared memory (bit-identical, coalesced, slower)
+    const int rpb = warp_band_rows(S);
+    dim3 bgrid((S + rpb - 1) / rpb, B);
+    if (set_smem_attr(ctx, reinterpret_cast<const void*>(warp_normalize_band_kernel<true, true>), kWarpBandStageBytes)) return 1;
+    if (set_smem_attr(ctx, reinterpret_cast<const void*>(warp_normalize_band_kernel<true, false>), kWarpBandStageBytes)) return 1;
+    if (set_smem_attr(ctx, reinterpret_cast<const void*>(warp_normalize_band_kernel<false, true>), kWarpBandStageBytes)) return 1;
+    if (d_out_u8 && d_out_bf16)
+      warp_normalize_band_kernel<true, true><<<bgrid, kWarpBandThreads, kWarpBandStageBytes, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+    else if (d_out_u8)
+      warp_normalize_band_kernel<true, false><<<bgrid, kWarpBandThreads, kWarpBandStageBytes, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+    else
+      warp_normalize_band_kernel<false, true><<<bgrid, kWarpBandThreads, kWarpBandStageBytes, st>>>(src, ctx->d_jobs, S, ctx->d_wtab, ctx->d_lut, o8, ob);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return ws_end(ctx, st);
   }
   dim3 grid((S * S + kWarpPixPerBlock - 1) / kWarpPixPerBlock, B);
   if (d_out_u8 && d_out_bf16)
@@ -1200,12 +1250,12 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
   return 0;
 }
 
-int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, float* d_norm, void* d_emb_bf16,
-                 cudaStream_t st) {
-  if (ctx->layers.empty()) return fail(ctx, "frb_embed: no backbone loaded");
-  const int Bn = (flags & FRB_EMBED_FLIP) ? 2 * B : B;  // faces through the network
+// Bn faces through the network in ONE pass of the layer program (no flip pairing here: l2 / renorm as given).
+int embed_chunk_locked(frb_ctx* ctx, const void* d_in, int Bn, int l2, int renorm, float* d_emb, float* d_norm,
+                       void* d_emb_bf16, cudaStream_t st) {
   const bool want_df = ctx->use_dataflow && !ctx->profiling;
-  if (ctx->plan.B != Bn || ctx->plan.d_in != d_in || ctx->plan.gp.empty() || ctx->plan.dataflow != want_df) {
+  // the plan bakes in the batch size only: the network input is read by the stem kernel through a plain pointer
+  if (ctx->plan.B != Bn || ctx->plan.gp.empty() || ctx->plan.dataflow != want_df) {
     ctx->plan.gp.clear();
     if (build_plan(ctx, Bn, d_in)) return 1;
     ctx->plan.d_in = d_in;
@@ -1269,36 +1319,56 @@ int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb,
       } else if (launch_conv(ctx, pl.block_n[i], pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
     } else if (L.op == FRB_OP_FC) {
       if (launch_gemm(ctx, 256, A_TILED, 1, pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
-      const bool flipf = (flags & FRB_EMBED_FLIP) != 0;
-      float* emb_dst = d_emb;
-      void* bf_dst = d_emb_bf16;
-      if (flipf) {
-        const size_t need = static_cast<size_t>(Bn) * 512;
-        if (ctx->emb2_elems < need) {
-          if (ctx->d_emb2) CK(cudaFree(ctx->d_emb2));
-          ctx->d_emb2 = nullptr;
-          CK(cudaMalloc(&ctx->d_emb2, need * 4));
-          ctx->emb2_elems = need;
-        }
-        emb_dst = ctx->d_emb2;
-        bf_dst = nullptr;
-      }
-      // with flip fusion each half is normalised the way extract_embeddings_batch(normalize=True) does
-      const int renorm = (flags & FRB_EMBED_RENORM) || flipf ? 1 : 0;
       fc_finalize_kernel<<<Bn, 128, 0, st>>>(ctx->d_fc_partial, pl.gp[i].num_splits, Bn,
-                                             reinterpret_cast<const float*>(blob + L.bias_off),
-                                             (flags & FRB_EMBED_L2) ? 1 : 0, renorm, emb_dst, flipf ? nullptr : d_norm,
-                                             reinterpret_cast<__nv_bfloat16*>(bf_dst));
+                                             reinterpret_cast<const float*>(blob + L.bias_off), l2, renorm, d_emb, d_norm,
+                                             reinterpret_cast<__nv_bfloat16*>(d_emb_bf16));
       CK(cudaGetLastError());
       ctx->launches++;
-      if (flipf) {
-        flip_fuse_kernel<<<B, 128, 0, st>>>(ctx->d_emb2, B, d_emb, reinterpret_cast<__nv_bfloat16*>(d_emb_bf16));
-        CK(cudaGetLastError());
-        ctx->launches++;
-      }
     }
   }
   if (ctx->profiling) CK(cudaEventRecord(ctx->prof_events[ctx->layers.size()], st));
+  return 0;
+}
+
+// B faces (2B crops with FRB_EMBED_FLIP).  Large batches go through the network in chunks of at most
+// ctx->embed_chunk faces (default 256; FRB_EMBED_CHUNK=0 disables): per face the network is FASTER at 256 than at
+// 1024 (21.3 vs 24.4 us measured) because a layer's output stays in the 126 MB L2 for the next layer only while
+// the activations of a chunk fit there.  A face's embedding does not depend on the batch it travels in
+// (tests/test_gpu_embed.py), so chunking changes no bit; chunks are equal-sized (one plan), the last one is
+// right-aligned and recomputes a few faces of its predecessor when the batch is not a multiple.
+int embed_locked(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, float* d_norm, void* d_emb_bf16,
+                 cudaStream_t st) {
+  if (ctx->layers.empty()) return fail(ctx, "frb_embed: no backbone loaded");
+  const bool flipf = (flags & FRB_EMBED_FLIP) != 0;
+  const int Bn = flipf ? 2 * B : B;  // faces through the network
+  float* emb_dst = d_emb;
+  float* norm_dst = d_norm;
+  void* bf_dst = d_emb_bf16;
+  if (flipf) {
+    if (ensure(ctx, &ctx->d_emb2, &ctx->emb2_elems, static_cast<size_t>(Bn) * 512)) return 1;
+    emb_dst = ctx->d_emb2;
+    norm_dst = nullptr;
+    bf_dst = nullptr;
+  }
+  const int l2 = (flags & FRB_EMBED_L2) ? 1 : 0;
+  // with flip fusion each half is normalised the way extract_embeddings_batch(normalize=True) does
+  const int renorm = ((flags & FRB_EMBED_RENORM) || flipf) ? 1 : 0;
+  const int limit = (ctx->profiling || ctx->embed_chunk <= 0) ? Bn : ctx->embed_chunk;
+  const int n_chunks = (Bn + limit - 1) / limit;
+  const int Bc = (Bn + n_chunks - 1) / n_chunks;
+  const size_t face_bytes = static_cast<size_t>(112) * 112 * 3 * 2;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int c0 = std::min(c * Bc, Bn - Bc);   // the last chunk is right-aligned
+    if (embed_chunk_locked(ctx, static_cast<const uint8_t*>(d_in) + c0 * face_bytes, Bc, l2, renorm,
+                           emb_dst ? emb_dst + static_cast<size_t>(c0) * 512 : nullptr, norm_dst ? norm_dst + c0 : nullptr,
+                           bf_dst ? static_cast<uint8_t*>(bf_dst) + static_cast<size_t>(c0) * 512 * 2 : nullptr, st))
+      return 1;
+  }
+  if (flipf) {
+    flip_fuse_kernel<<<B, 128, 0, st>>>(ctx->d_emb2, B, d_emb, reinterpret_cast<__nv_bfloat16*>(d_emb_bf16));
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
   return 0;
 }
 
@@ -1555,6 +1625,8 @@ int match_workspace(frb_ctx* ctx, int P) {
 // Match P prepared probes (fp32 + bf16 copies, normalised as search() does) against the resident gallery.  Everything
 // is enqueued on `st`; nothing here waits for the device.  push != nullptr: identity-sharded match, finished rows
 // also go to the peers' exchange buffers.
+// The caller has zeroed the match counters (ctx->d_match_ctr[0..1]) on `st` BEFORE its probe kernel: nothing but
+// kernels may sit between the probe kernel and the filter, or the programmatic launch edge between them is lost.
 int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_probe_bf16, int P, int k, float thr,
                float* d_scores, long long* d_idx, unsigned char* d_accept, double* s64, const PeerPush* push,
                cudaStream_t st) {
@@ -1562,8 +1634,6 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
   PeerPush no_push;
   memset(&no_push, 0, sizeof(no_push));
   const PeerPush& pp = push ? *push : no_push;
-  // device counters of this match: flagged rows, rows pushed
-  CK(cudaMemsetAsync(ctx->d_match_ctr, 0, 8, st));
   if (N == 0 || N < kExactOnlyBelow || k > kExactMaxK) {
     if (N == 0) {
       match_fill_empty_kernel<<<(P * k + 255) / 256, 256, 0, st>>>(P, k, s64, d_idx, d_scores, d_accept);
@@ -1626,24 +1696,20 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
   CUtensorMap tmP;
   if (make_tmap_2d(ctx, &tmP, d_probe_bf16, 512, static_cast<uint64_t>(P), 128)) return 1;
   if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[1], st));
+  // The four kernels of the chain are launched with programmatic stream serialization: each sets itself up while its
+  // predecessor drains and blocks in griddepcontrol.wait before it reads the predecessor's output.  In the plain
+  // match the filter's predecessor is probe_prepare_kernel (which releases its dependents at once); in the sharded
+  // match it is xchg_wait_kernel (no early release: the filter waits for its completion).
+  const bool pdl = ctx->use_pdl != 0 && !ctx->match_profiling;   // an event between two launches breaks the programmatic edge
   if (pair_mode) {
     if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_filter2_kernel), Match2Smem::kTotal)) return 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(std::min(mp.p_tiles * mp.slices, units) * 2);
-    cfg.blockDim = dim3(kMatch2Threads);
-    cfg.dynamicSmemBytes = Match2Smem::kTotal;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    fill_launch_attrs(attr, 2);
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, match_filter2_kernel, tmP, ctx->tmG2, mp));
+    CK(launch_pdl(match_filter2_kernel, dim3(std::min(mp.p_tiles * mp.slices, units) * 2), dim3(kMatch2Threads), Match2Smem::kTotal, st,
+                  pdl, 2, tmP, ctx->tmG2, mp));
   } else {
     if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_filter_kernel), MatchSmem::kTotal)) return 1;
-    const int grid = std::min(mp.p_tiles * mp.slices, ctx->num_sms);
-    match_filter_kernel<<<grid, kMatchThreads, MatchSmem::kTotal, st>>>(tmP, ctx->tmG, mp);
+    CK(launch_pdl(match_filter_kernel, dim3(std::min(mp.p_tiles * mp.slices, ctx->num_sms)), dim3(kMatchThreads), MatchSmem::kTotal, st,
+                  pdl, 1, tmP, ctx->tmG, mp));
   }
-  CK(cudaGetLastError());
   ctx->launches++;
   if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[2], st));
   FinalizeParams fp;
@@ -1653,8 +1719,7 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
   fp.out_score = s64; fp.out_idx = d_idx; fp.out_score_f32 = d_scores; fp.out_accept = d_accept;
   fp.flagged = ctx->d_flagged; fp.flag_rows = ctx->d_flag_rows; fp.flag_count = ctx->d_match_ctr;
   fp.push = pp;
-  match_finalize_kernel<<<P, 128, 0, st>>>(fp);
-  CK(cudaGetLastError());
+  CK(launch_pdl(match_finalize_kernel, dim3(P), dim3(128), 0, st, pdl, 1, fp));
   ctx->launches++;
   // Rows whose proof failed get the exact scan.  Rare (none on the synthetic workloads), so the two kernels are
   // launched unconditionally and take the row list and its length from the device: no D2H, no synchronisation.
@@ -1663,11 +1728,9 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
   xp.k = k; xp.thr = thr; xp.first_global_id = ctx->gal_first; xp.part = ctx->d_exact_part;
   xp.out_score = s64; xp.out_idx = d_idx; xp.out_score_f32 = d_scores; xp.out_accept = d_accept;
   xp.push = pp;
-  match_exact_part_kernel<<<dim3(kExactBlocks, std::min(P, kExactRowsY)), 256, 0, st>>>(xp);
-  CK(cudaGetLastError());
+  CK(launch_pdl(match_exact_part_kernel, dim3(kExactBlocks, std::min(P, kExactRowsY)), dim3(256), 0, st, pdl, 1, xp));
   ctx->launches++;
-  match_exact_fix_kernel<<<std::min(P, 64), 128, 0, st>>>(xp, kExactBlocks);
-  CK(cudaGetLastError());
+  CK(launch_pdl(match_exact_fix_kernel, dim3(std::min(P, 64)), dim3(128), 0, st, pdl, 1, xp, static_cast<int>(kExactBlocks)));
   ctx->launches++;
   if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[3], st));
   // frb_match_last_flagged: the count travels to pinned memory behind an event, read only when somebody asks
@@ -1694,6 +1757,7 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
   if (match_workspace(ctx, P)) return 1;
   double* s64 = d_scores64;
   if (!s64 && scores64_scratch(ctx, static_cast<size_t>(P) * k, &s64)) return 1;
+  CK(cudaMemsetAsync(ctx->d_match_ctr, 0, 8, st));   // device counters of this match: flagged rows, rows pushed
   if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[0], st));
   probe_prepare_kernel<<<P, 128, 0, st>>>(d_probes, normalize, ctx->d_probe_f32, ctx->d_probe_bf16);
   CK(cudaGetLastError());
@@ -2084,7 +2148,7 @@ extern "C" int frb_match_sharded(frb_ctx* ctx, const float* d_local_probes, int 
   if (scores64_scratch(ctx, static_cast<size_t>(P_total) * k, &s64)) return 1;
   const unsigned epoch = ++x.epoch;
   const int G = x.world;
-  CK(cudaMemsetAsync(ctx->d_match_ctr + 2, 0, 4, st));
+  CK(cudaMemsetAsync(ctx->d_match_ctr, 0, 12, st));   // flagged rows, rows pushed, probe rows pushed
   // 1. probes -> everyone
   ProbePush pq;
   memset(&pq, 0, sizeof(pq));

@@ -5,14 +5,14 @@
 // pair-tiles on 74 pairs).  As in gemm2_multi_sm100.cuh the CTA pairs stay resident for the whole run: a tile of
 // layer l+1 starts when its image is complete in layer l (per-image progress counters), tiles are dealt round-robin
 // across layers, TMEM / the slab ring / barrier phases carry over.  What is specific to this kernel: the weights are
-// RESIDENT in shared memory (36-147 KB per CTA), so they are swapped at every layer boundary — the MMA warp releases
-// them with one commit after its last MMA of the layer (w_free), the producer first pre-fills the slab ring with the
-// next layer's first units (they do not depend on the weights), then refills the weights.
-//
-// MEASURED (tools/run_r2j.sh, batch 256): bit-identical at batch 8 / 256 / 1024, but the embed is 0.35 ms SLOWER than
-// with one launch per slab layer — the weight swap (~4-5 us with the tensor pipe idle, every CTA at once) costs more
-// than the drain it removes, because separate launches prefetch their weights under the previous layer's tail.
-// Kept behind FRB_SLAB_MULTI=1 (off); it needs double-buffered weights to pay off, which only the Cin = 64 layers can fit.
+// RESIDENT in shared memory (36-147 KB per CTA: no room for a second copy), so they are swapped at every layer
+// boundary.  Round 1 released them with ONE commit after the layer's last MMA and then refilled all 18 K blocks with
+// the tensor pipe idle (~4-5 us per boundary, every CTA at once: 0.35 ms slower per batch-256 embed than one launch
+// per layer, profiles/r01d).  Now the swap is STREAMED through the pair's last tile of the layer: in that tile the
+// MMA warp commits a per-K-block barrier (b_free[i]) right after the four MMAs that read weight block i for the last
+// time, and the producer refills block i with the next layer's weights as soon as that barrier completes - while the
+// remaining taps of the tile still run.  The first tile of the next layer waits per unit (9 K blocks) for its weights,
+// which were requested one to two tile-times earlier.
 //
 // All layers of a run share geometry (B, H, W, R, Cin, Cout) and buffer layout, so image-complete dependencies cover
 // read-after-write and write-after-read (see gemm2_multi_sm100.cuh).  Per-tile instruction streams are those of
@@ -44,7 +44,7 @@ conv_slab_multi_sm100_kernel(const SlabLayer* __restrict__ layers, int num_layer
   uint64_t* slab_full = bars;                             // [6]  leader only
   uint64_t* slab_empty = bars + kSlabMaxBuf;              // [6]  per CTA
   uint64_t* b_full = bars + 2 * kSlabMaxBuf;              // [18] leader only
-  uint64_t* w_free = b_full + kSlabMaxBStages;            // [1]  per CTA: the layer's MMAs no longer read the weights
+  uint64_t* b_free = b_full + kSlabMaxBStages;            // [18] per CTA: the layer's MMAs no longer read weight block i
   uint64_t* tmem_full_bar = b_full + 2 * kSlabMaxBStages; // [4] per CTA   (same offsets as conv_slab_sm100_kernel)
   uint64_t* tmem_empty_bar = tmem_full_bar + 4;           // [4] leader only, 16 arrivals
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 4);
@@ -71,8 +71,10 @@ conv_slab_multi_sm100_kernel(const SlabLayer* __restrict__ layers, int num_layer
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 16);
     }
-    for (int i = 0; i < kSlabMaxBStages; ++i) mbar_init(&b_full[i], 1);
-    mbar_init(w_free, 1);
+    for (int i = 0; i < kSlabMaxBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_free[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -139,12 +141,12 @@ conv_slab_multi_sm100_kernel(const SlabLayer* __restrict__ layers, int num_layer
         }
         pdl_wait();
       } else {
-        // pre-fill the slab ring with this layer's first units (independent of the weights), then swap the weights
-        // as soon as the pair's MMAs of the previous layer have retired
-        while (next < n_units && mbar_test(&slab_empty[nbuf_i], nphase ^ 1)) issue_unit();
-        mbar_wait(w_free, static_cast<uint32_t>((l - 1) & 1));
+        // weight block i is refilled as soon as the previous layer's last tile has used it (b_free[i]); in between,
+        // this layer's first slab units (independent of the weights) go out whenever a slab buffer is free
         for (int i = 0; i < kNumKb; ++i) {
           const int cc = i / 9, tap = i - cc * 9;
+          while (next < n_units && mbar_test(&slab_empty[nbuf_i], nphase ^ 1)) issue_unit();
+          mbar_wait(&b_free[i], static_cast<uint32_t>((l - 1) & 1));
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(&b_full[i], 2 * kBBytes);
             tma2_load_2d(&L->tmB, b_full_leader0 + 8 * i, smem_b + i * kBBytes, (tap * CHUNKS + cc) * kBlockK, crank * (BLOCK_N / 2));
@@ -175,27 +177,54 @@ conv_slab_multi_sm100_kernel(const SlabLayer* __restrict__ layers, int num_layer
       for (int l = 0; l < num_layers; ++l) {
         const int n_iters = iters_of(first_pair_of(rot));
         rot = (rot + total_pairs) % pair_step;
-        for (int i = 0; i < kNumKb; ++i) mbar_wait(&b_full[i], static_cast<uint32_t>(l & 1));  // this layer's weights
-        tc_fence_after();
+        if (n_iters == 0) {
+          // no tile of this layer for this pair (small batches): its weights still pass through shared memory, so
+          // wait until they have landed, then hand every block back (a commit with nothing outstanding arrives at once)
+          for (int i = 0; i < kNumKb; ++i) mbar_wait(&b_full[i], static_cast<uint32_t>(l & 1));
+          if (elect_one()) {
+#pragma unroll
+            for (int i = 0; i < kNumKb; ++i) umma2_commit_pair(&b_free[i]);
+          }
+          __syncwarp();
+        }
         for (int it = 0; it < n_iters; ++it) {
+          const bool last = (it == n_iters - 1);   // the pair's last tile of this layer: releases the weights block by block
           mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
           const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
 #pragma unroll
           for (int cc = 0; cc < CHUNKS; ++cc) {
             mbar_wait(&slab_full[buf], sphase);
+            if (it == 0)   // first tile: this unit's nine weight blocks of the new layer
+              for (int tap = 0; tap < 9; ++tap) mbar_wait(&b_full[cc * 9 + tap], static_cast<uint32_t>(l & 1));
             tc_fence_after();
             const uint32_t a_lo = slab_lo0 + buf * slab_step;
-            if (elect_one()) {
+            if (!last) {
+              if (elect_one()) {
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                const uint32_t b_lo = b_lo0 + (cc * 9 + tap) * (kBBytes >> 4);
-                const uint32_t a_tap = a_lo + (tap / 3) * wp8 + (tap % 3) * 8;
+                for (int tap = 0; tap < 9; ++tap) {
+                  const uint32_t b_lo = b_lo0 + (cc * 9 + tap) * (kBBytes >> 4);
+                  const uint32_t a_tap = a_lo + (tap / 3) * wp8 + (tap % 3) * 8;
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k)
-                  umma2_bf16_ss_lo(tmem_d, a_tap + 2 * k, b_lo + 2 * k, desc_hi, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma2_bf16_ss_lo(tmem_d, a_tap + 2 * k, b_lo + 2 * k, desc_hi, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
+                umma2_commit_pair(&slab_empty[buf]);
+                if (cc == CHUNKS - 1) umma2_commit_pair(&tmem_full_bar[acc]);
               }
-              umma2_commit_pair(&slab_empty[buf]);
-              if (cc == CHUNKS - 1) umma2_commit_pair(&tmem_full_bar[acc]);
+            } else {
+              if (elect_one()) {
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                  const uint32_t b_lo = b_lo0 + (cc * 9 + tap) * (kBBytes >> 4);
+                  const uint32_t a_tap = a_lo + (tap / 3) * wp8 + (tap % 3) * 8;
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma2_bf16_ss_lo(tmem_d, a_tap + 2 * k, b_lo + 2 * k, desc_hi, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  umma2_commit_pair(&b_free[cc * 9 + tap]);   // weight block (cc, tap) has been read for the last time
+                }
+                umma2_commit_pair(&slab_empty[buf]);
+                if (cc == CHUNKS - 1) umma2_commit_pair(&tmem_full_bar[acc]);
+              }
             }
             __syncwarp();
             if (++buf == g.nbuf) {
@@ -208,9 +237,6 @@ conv_slab_multi_sm100_kernel(const SlabLayer* __restrict__ layers, int num_layer
             acc_phase ^= 1;
           }
         }
-        // every MMA of this layer (in this pair) has been issued: their retirement frees the resident weights
-        if (elect_one()) umma2_commit_pair(w_free);
-        __syncwarp();
       }
     }
   } else {

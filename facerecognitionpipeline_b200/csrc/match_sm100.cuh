@@ -146,9 +146,11 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
 
   // Producer and MMA warps run CONVERGED; every wait is outside the elect.sync regions that issue TMA / UTCHMMA, so
   // ptxas emits bare back-to-back instructions (see conv_slab_sm100.cuh for the measurement behind this).
+  pdl_launch_dependents();
   if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0, a_phase = 0;
+    pdl_wait();   // the probes come from the kernel launched just before (programmatic stream serialization)
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int pt = item % p.p_tiles;
       const int gs = item / p.p_tiles;
@@ -362,6 +364,7 @@ match_filter2_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ---- TMA producer (both CTAs): own probe tile + own half of every gallery tile, completing on the leader's barriers
@@ -369,6 +372,7 @@ match_filter2_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
     const uint32_t b_full_leader0 = mapa_u32(smem_u32(&b_full[0]), 0);
     int stage = 0;
     uint32_t phase = 0, a_phase = 0;
+    pdl_wait();   // the probes come from the kernel launched just before (programmatic stream serialization)
     for (int item = first_item; item < total_items; item += item_step) {
       const int pt = (item % p.p_tiles) * 2 + crank;
       const int gs = item / p.p_tiles;

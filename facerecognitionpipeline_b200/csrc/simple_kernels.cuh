@@ -325,6 +325,255 @@ warp_normalize_staged_kernel(const uint8_t* __restrict__ src_base, const WarpJob
   }
 }
 
+// ---- band-staged variant (round 2; FRB_WARP_BAND=1, off: measured 3x slower than the direct gather): one block = one band of whole output rows (~2048 pixels) of one face.
+// The band's source footprint is a parallelogram; for every source row the block records the exact pixel span its
+// taps touch (computed from the SAME fixed-point coordinates the gather uses), copies those spans - and nothing else -
+// into shared memory with 16-byte loads that keep their global alignment phase, and gathers the 2x2 taps from there.
+// ~30 KB per block instead of the ~200 KB of the whole-face variant above, so 4-5 blocks share an SM and the copy of
+// one overlaps the gather of another.  Global memory sees every source byte of a band once, in 16-byte pieces, instead
+// of the 10.8 sectors per request of the direct gather.  Pixels whose taps leave the image (or whose rows did not fit
+// the staging buffer) take the same global paths as warp_normalize_kernel: identical arithmetic, identical bytes out.
+constexpr int kWarpBandThreads = 256;
+constexpr int kWarpBandMaxRows = 224;             // source rows a band may stage
+constexpr int kWarpBandStageBytes = 36 * 1024;    // dynamic shared memory for the staged spans (+16 slack inside)
+__host__ __device__ __forceinline__ int warp_band_rows(int S) { return kWarpPixPerBlock / S > 0 ? kWarpPixPerBlock / S : 1; }
+
+template <bool kWriteU8, bool kWriteBf16>
+__global__ void __launch_bounds__(kWarpBandThreads)
+warp_normalize_band_kernel(const uint8_t* __restrict__ src_base, const WarpJob* __restrict__ jobs, int S,
+                           const unsigned short* __restrict__ wtab_g, const unsigned short* __restrict__ lut_g,
+                           uint8_t* __restrict__ out_u8, __nv_bfloat16* __restrict__ out_bf16) {
+  extern __shared__ __align__(16) uint8_t s_stage[];
+  __shared__ double s_m[6];
+  __shared__ WarpJob s_job;
+  __shared__ __align__(8) unsigned short wtab[kInterTab * kInterTab * 4];
+  __shared__ unsigned short lut[256];
+  __shared__ int s_adelta[kWarpMaxS], s_bdelta[kWarpMaxS], s_X0[kWarpMaxRows], s_Y0[kWarpMaxRows];
+  __shared__ int s_xs[kWarpBandMaxRows], s_xe[kWarpBandMaxRows];   // staged pixel span of source row Ysrc0 + i (xe < xs: none)
+  __shared__ int s_delta[kWarpBandMaxRows];                        // s_stage offset of (that row's pixel 0)
+  __shared__ int s_cstart[kWarpBandMaxRows + 1];                   // prefix sums of the rows' 16-byte chunk counts
+  __shared__ int s_ysrc0, s_nrows;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < kInterTab * kInterTab; i += kWarpBandThreads)
+    reinterpret_cast<uint2*>(wtab)[i] = __ldg(reinterpret_cast<const uint2*>(wtab_g) + i);
+  if (tid < 256) lut[tid] = lut_g[tid];
+  const int face = blockIdx.y;
+  if (tid == 0) {
+    const WarpJob jb = jobs[face];
+    s_job = jb;
+    double D = __dsub_rn(__dmul_rn(jb.M[0], jb.M[4]), __dmul_rn(jb.M[1], jb.M[3]));
+    D = (D != 0.0) ? __ddiv_rn(1.0, D) : 0.0;
+    const double A11 = __dmul_rn(jb.M[4], D), A22 = __dmul_rn(jb.M[0], D);
+    const double m00 = A11;
+    const double m01 = __dmul_rn(jb.M[1], -D);
+    const double m10 = __dmul_rn(jb.M[3], -D);
+    const double m11 = A22;
+    s_m[0] = m00; s_m[1] = m01; s_m[2] = m10; s_m[3] = m11;
+    s_m[4] = __dsub_rn(__dmul_rn(-m00, jb.M[2]), __dmul_rn(m01, jb.M[5]));
+    s_m[5] = __dsub_rn(__dmul_rn(-m10, jb.M[2]), __dmul_rn(m11, jb.M[5]));
+  }
+  for (int i = tid; i < kWarpBandMaxRows; i += kWarpBandThreads) {
+    s_xs[i] = 0x7fffffff;
+    s_xe[i] = -1;
+  }
+  __syncthreads();
+  const int srcH = s_job.H, srcW = s_job.W, pitch = s_job.pitch;
+  const uint8_t* img = src_base + s_job.src_off;
+  const uint8_t* img_end = img + static_cast<size_t>(srcH) * pitch;
+  const int rows_per_band = warp_band_rows(S);
+  const int y_first = blockIdx.x * rows_per_band;
+  const int y_last = min(S, y_first + rows_per_band) - 1;
+  const int pix_begin = y_first * S, pix_end = (y_last + 1) * S;
+  {
+    const double m00 = s_m[0], m01 = s_m[1], m10 = s_m[2], m11 = s_m[3], b1 = s_m[4], b2 = s_m[5];
+    const int round_delta = kAbScale / kInterTab / 2;
+    for (int x = tid; x < S; x += kWarpBandThreads) {
+      s_adelta[x] = cv_round_sat(__dmul_rn(__dmul_rn(m00, (double)x), (double)kAbScale));
+      s_bdelta[x] = cv_round_sat(__dmul_rn(__dmul_rn(m10, (double)x), (double)kAbScale));
+    }
+    for (int r = tid; r <= y_last - y_first; r += kWarpBandThreads) {
+      const int y = y_first + r;
+      s_X0[r] = cv_round_sat(__dmul_rn(__dadd_rn(__dmul_rn(m01, (double)y), b1), (double)kAbScale)) + round_delta;
+      s_Y0[r] = cv_round_sat(__dmul_rn(__dadd_rn(__dmul_rn(m11, (double)y), b2), (double)kAbScale)) + round_delta;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // source rows of the band: sy is monotone in x and in y, so its extremes sit at the band's corner pixels
+    int lo = 0x7fffffff, hi = -0x7fffffff;
+    for (int c = 0; c < 4; ++c) {
+      const int x = (c & 1) ? S - 1 : 0, r = (c & 2) ? y_last - y_first : 0;
+      const int sy = (s_Y0[r] + s_bdelta[x]) >> kAbBits;
+      lo = min(lo, sy);
+      hi = max(hi, sy + 1);
+    }
+    lo = max(lo, 0);
+    hi = min(hi, srcH - 1);
+    s_ysrc0 = lo;
+    s_nrows = (hi >= lo) ? min(hi - lo + 1, kWarpBandMaxRows) : 0;
+  }
+  __syncthreads();
+  const int ysrc0 = s_ysrc0, nrows = s_nrows;
+  // ---- pass 1: the pixel span every source row needs (interior taps only; the rest never reads shared memory)
+  for (int pix0 = pix_begin + (tid & ~31); pix0 < pix_end; pix0 += kWarpBandThreads) {
+    const int pix = pix0 + lane;
+    int sx = 0, sy = -0x40000000;
+    bool interior = false;
+    if (pix < pix_end) {
+      const int y = pix / S, x = pix - y * S;
+      sx = (s_X0[y - y_first] + s_adelta[x]) >> kAbBits;
+      sy = (s_Y0[y - y_first] + s_bdelta[x]) >> kAbBits;
+      interior = sx >= 0 && sx + 3 <= srcW && sy >= 0 && sy + 1 < srcH && sy - ysrc0 >= 0 && sy + 1 - ysrc0 < nrows;
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, interior);
+    if (interior) {
+      const unsigned grp = __match_any_sync(act, sy);      // lanes of this warp that read the same two source rows
+      const int lo = __reduce_min_sync(grp, sx), hi = __reduce_max_sync(grp, sx) + 1;
+      if (lane == __ffs(grp) - 1) {
+        const int i = sy - ysrc0;
+        atomicMin(&s_xs[i], lo); atomicMax(&s_xe[i], hi);
+        atomicMin(&s_xs[i + 1], lo); atomicMax(&s_xe[i + 1], hi);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- pass 2: lay the spans out as 16-byte chunks that keep their global alignment phase
+  if (tid < 32) {
+    int carry = 0;
+    for (int base = 0; base < nrows; base += 32) {
+      const int i = base + lane;
+      int nch = 0;
+      if (i < nrows && s_xe[i] >= s_xs[i]) {
+        const uintptr_t g0 = reinterpret_cast<uintptr_t>(img) + static_cast<size_t>(ysrc0 + i) * pitch + 3 * s_xs[i];
+        const uintptr_t g1 = reinterpret_cast<uintptr_t>(img) + static_cast<size_t>(ysrc0 + i) * pitch + 3 * (s_xe[i] + 1);
+        nch = static_cast<int>((g1 - (g0 & ~static_cast<uintptr_t>(15)) + 15) >> 4);
+      }
+      int incl = nch;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int start = carry + incl - nch;
+      if (i < nrows) {
+        if ((start + nch) * 16 + 16 > kWarpBandStageBytes) {   // does not fit: this row is not staged (global path)
+          s_xs[i] = 0x7fffffff;
+          s_xe[i] = -1;
+          nch = 0;
+        }
+      }
+      // rows dropped for capacity keep the layout of the rows before them intact: recompute the inclusive scan
+      incl = nch;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      start = carry + incl - nch;
+      if (i < nrows) {
+        s_cstart[i] = start;
+        if (nch > 0) {
+          const uintptr_t g0 = reinterpret_cast<uintptr_t>(img) + static_cast<size_t>(ysrc0 + i) * pitch + 3 * s_xs[i];
+          s_delta[i] = start * 16 + static_cast<int>(g0 & 15) - 3 * s_xs[i];
+        }
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_cstart[nrows] = carry;
+  }
+  __syncthreads();
+  // ---- pass 3: copy (four 16-byte requests in flight per thread before the first is stored)
+  {
+    const int total = s_cstart[nrows];
+    constexpr int kUnroll = 4;
+    for (int c0 = tid; c0 < total; c0 += kWarpBandThreads * kUnroll) {
+      uint4 v[kUnroll];
+      int dst[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int c = c0 + u * kWarpBandThreads;
+        dst[u] = -1;
+        v[u] = make_uint4(0, 0, 0, 0);
+        if (c < total) {
+          int lo = 0, hi = nrows - 1;             // the row whose chunk range contains c
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_cstart[mid] <= c) lo = mid; else hi = mid - 1;
+          }
+          const int i = lo, k = c - s_cstart[i];
+          const uintptr_t g0 = reinterpret_cast<uintptr_t>(img) + static_cast<size_t>(ysrc0 + i) * pitch + 3 * s_xs[i];
+          const uint8_t* ga = reinterpret_cast<const uint8_t*>(g0 & ~static_cast<uintptr_t>(15)) + k * 16;
+          dst[u] = c * 16;
+          if (ga >= img && ga + 16 <= img_end) {
+            v[u] = __ldg(reinterpret_cast<const uint4*>(ga));
+          } else {  // chunk straddles the first / last bytes of the image: never read outside it
+            unsigned char t[16];
+#pragma unroll
+            for (int b = 0; b < 16; ++b) t[b] = (ga + b >= img && ga + b < img_end) ? ga[b] : 0;
+            v[u].x = t[0] | (t[1] << 8) | (t[2] << 16) | (static_cast<uint32_t>(t[3]) << 24);
+            v[u].y = t[4] | (t[5] << 8) | (t[6] << 16) | (static_cast<uint32_t>(t[7]) << 24);
+            v[u].z = t[8] | (t[9] << 8) | (t[10] << 16) | (static_cast<uint32_t>(t[11]) << 24);
+            v[u].w = t[12] | (t[13] << 8) | (t[14] << 16) | (static_cast<uint32_t>(t[15]) << 24);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (dst[u] >= 0) *reinterpret_cast<uint4*>(s_stage + dst[u]) = v[u];
+    }
+  }
+  __syncthreads();
+  // ---- pass 4: gather
+  for (int pix = pix_begin + tid; pix < pix_end; pix += kWarpBandThreads) {
+    const int y = pix / S, x = pix - y * S;
+    const int X = (s_X0[y - y_first] + s_adelta[x]) >> (kAbBits - kInterBits);
+    const int Y = (s_Y0[y - y_first] + s_bdelta[x]) >> (kAbBits - kInterBits);
+    const int sx = X >> kInterBits, sy = Y >> kInterBits;
+    const int ax = X & (kInterTab - 1), ay = Y & (kInterTab - 1);
+    const ushort4 w4 = reinterpret_cast<const ushort4*>(wtab)[ay * kInterTab + ax];
+    const int4 w = make_int4(w4.x, w4.y, w4.z, w4.w);
+    int acc0 = 0, acc1 = 0, acc2 = 0;
+    if (sx >= 0 && sx + 3 <= srcW && sy >= 0 && sy + 1 < srcH) {
+      uint32_t lo0, hi0, lo1, hi1;
+      const int i = sy - ysrc0;
+      if (i >= 0 && i + 1 < nrows && sx >= s_xs[i] && sx + 1 <= s_xe[i] && sx >= s_xs[i + 1] && sx + 1 <= s_xe[i + 1]) {
+        warp_load6_smem(s_stage + s_delta[i] + 3 * sx, &lo0, &hi0);
+        warp_load6_smem(s_stage + s_delta[i + 1] + 3 * sx, &lo1, &hi1);
+      } else {   // rows that did not fit the staging buffer
+        const uint8_t* q0 = img + static_cast<size_t>(sy) * pitch + 3 * sx;
+        warp_load6(q0, &lo0, &hi0);
+        warp_load6(q0 + pitch, &lo1, &hi1);
+      }
+      acc0 = w.x * (lo0 & 0xff) + w.y * (lo0 >> 24) + w.z * (lo1 & 0xff) + w.w * (lo1 >> 24);
+      acc1 = w.x * ((lo0 >> 8) & 0xff) + w.y * (hi0 & 0xff) + w.z * ((lo1 >> 8) & 0xff) + w.w * (hi1 & 0xff);
+      acc2 = w.x * ((lo0 >> 16) & 0xff) + w.y * ((hi0 >> 8) & 0xff) + w.z * ((lo1 >> 16) & 0xff) + w.w * ((hi1 >> 8) & 0xff);
+    } else {
+      const bool x0ok = (sx >= 0 && sx < srcW), x1ok = (sx + 1 >= 0 && sx + 1 < srcW);
+      if (sy >= 0 && sy < srcH) {
+        const uint8_t* rowp = img + static_cast<size_t>(sy) * pitch;
+        if (x0ok) { const uint8_t* q = rowp + 3 * sx; acc0 += w.x * q[0]; acc1 += w.x * q[1]; acc2 += w.x * q[2]; }
+        if (x1ok) { const uint8_t* q = rowp + 3 * (sx + 1); acc0 += w.y * q[0]; acc1 += w.y * q[1]; acc2 += w.y * q[2]; }
+      }
+      if (sy + 1 >= 0 && sy + 1 < srcH) {
+        const uint8_t* rowp = img + static_cast<size_t>(sy + 1) * pitch;
+        if (x0ok) { const uint8_t* q = rowp + 3 * sx; acc0 += w.z * q[0]; acc1 += w.z * q[1]; acc2 += w.z * q[2]; }
+        if (x1ok) { const uint8_t* q = rowp + 3 * (sx + 1); acc0 += w.w * q[0]; acc1 += w.w * q[1]; acc2 += w.w * q[2]; }
+      }
+    }
+    const int r8 = min(255, max(0, (acc0 + (1 << 14)) >> 15));
+    const int g8 = min(255, max(0, (acc1 + (1 << 14)) >> 15));
+    const int b8 = min(255, max(0, (acc2 + (1 << 14)) >> 15));
+    const size_t o = (static_cast<size_t>(face) * S * S + pix) * 3;
+    if (kWriteU8) {
+      out_u8[o] = (uint8_t)r8; out_u8[o + 1] = (uint8_t)g8; out_u8[o + 2] = (uint8_t)b8;
+    }
+    if (kWriteBf16) {
+      unsigned short* ob = reinterpret_cast<unsigned short*>(out_bf16) + o;
+      ob[0] = lut[b8]; ob[1] = lut[g8]; ob[2] = lut[r8];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ preprocess (aligned crops)
 // in: [B][S][S][3] RGB u8, S in {112, 224}.  224 -> 112 is cv2.resize INTER_LINEAR at exactly
 // 2x, which equals the 2x2 box mean rounded half up.  flip: also emit the horizontally flipped
@@ -617,6 +866,7 @@ probe_prepare_kernel(const float* __restrict__ in, int normalize, float* __restr
                      __nv_bfloat16* __restrict__ out_bf16) {
   const int b = blockIdx.x, t = threadIdx.x;
   __shared__ float red[4];
+  pdl_launch_dependents();   // the filter kernel may set itself up (barriers, TMEM, tensor maps) while this runs
   float x[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) x[j] = in[static_cast<size_t>(b) * 512 + t + 128 * j];
@@ -780,6 +1030,8 @@ match_finalize_kernel(const FinalizeParams p) {
   __shared__ float s_excl;
   __shared__ int s_flag;
   const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  pdl_launch_dependents();
+  pdl_wait();   // launched with programmatic stream serialization: the filter's candidate lists are complete from here
   const int C = p.slices * kCand;
   int Cp = 64;
   while (Cp < C) Cp <<= 1;
@@ -1061,6 +1313,8 @@ match_exact_part_kernel(const ExactFixParams p) {
   __shared__ float s_probe[512];
   __shared__ double w_sc[8][kExactMaxK];
   __shared__ long long w_ix[8][kExactMaxK];
+  pdl_launch_dependents();
+  pdl_wait();
   const int count = *p.count;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, k = p.k;
   for (int f = blockIdx.y; f < count; f += gridDim.y) {
@@ -1113,6 +1367,8 @@ match_exact_fix_kernel(const ExactFixParams p, int parts) {
   __shared__ long long s_besti[128];
   __shared__ double s_out[kExactMaxK];
   __shared__ long long s_outi[kExactMaxK];
+  pdl_launch_dependents();
+  pdl_wait();
   const int count = *p.count;
   const int t = threadIdx.x, k = p.k;
   for (int f = blockIdx.x; f < count; f += gridDim.x) {

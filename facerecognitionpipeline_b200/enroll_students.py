@@ -73,7 +73,8 @@ class StudentEnrollment:
     def __init__(self, gallery_path=PROJECT_ROOT / "gallery" / "students.pkl", min_faces_per_student=3,
                  max_faces_per_student=5, limit_images=0, image_indices=None, model_type="adaface",
                  architecture="ir_101", *, face_processor=None, detector=None, embedder=None, gallery=None,
-                 verbose: bool = True):
+                 verbose: bool = True, window_crops: int = 2048):
+        self.window_crops = int(window_crops)   # crops collected on the host before a window is embedded + registered
         self.min_faces = min_faces_per_student
         self.max_faces = max_faces_per_student
         self.limit_images = limit_images
@@ -182,23 +183,40 @@ class StudentEnrollment:
         if not student_dirs:
             self._say("No student directories found!")
             return {"error": "no_directories"}
-        # host pass over every student, then ONE stream of device batches over all crops
-        collected = [self.collect_student_faces(d) for d in student_dirs]
-        all_crops = [c for work, _ in collected if work is not None for c in work["crops"]]
-        all_emb = self.embedder.extract_embeddings_batch(all_crops, normalize=True) if all_crops else np.zeros((0, 512), np.float32)
-        results, successful, failed, at = [], 0, 0, 0
-        for student_dir, (work, info) in zip(student_dirs, collected):
-            if work is None:
-                ok = False
-            else:
-                n = len(work["crops"])
-                # ids follow the gallery's size at the time the student is added, like the reference's
-                # per-student loop (re-enrolling an existing name overwrites under a NEW id there too)
-                ok, info = self._register(student_dir, self._next_student_id(), work, all_emb[at:at + n])
-                at += n
-            successful += int(ok)
-            failed += int(not ok)
-            results.append({"directory": student_dir, "success": ok, "info": info})
+        # Students are collected on the host and embedded in bounded WINDOWS (about `window_crops` crops, ~150 KB each):
+        # the device still sees large batches, host memory no longer grows with the enrollment tree, and every window
+        # is registered before the next one is read, so a late failure loses one window, not everything.
+        results, successful, failed = [], 0, 0
+        window: List[Tuple[str, Optional[Dict], Dict]] = []
+        queued = 0
+
+        def flush():
+            nonlocal successful, failed, queued
+            crops = [c for _, work, _ in window if work is not None for c in work["crops"]]
+            emb = self.embedder.extract_embeddings_batch(crops, normalize=True) if crops else np.zeros((0, 512), np.float32)
+            at = 0
+            for student_dir, work, info in window:
+                if work is None:
+                    ok = False
+                else:
+                    n = len(work["crops"])
+                    # ids follow the gallery's size at the time the student is added, like the reference's
+                    # per-student loop (re-enrolling an existing name overwrites under a NEW id there too)
+                    ok, info = self._register(student_dir, self._next_student_id(), work, emb[at:at + n])
+                    at += n
+                successful += int(ok)
+                failed += int(not ok)
+                results.append({"directory": student_dir, "success": ok, "info": info})
+            window.clear()
+            queued = 0
+
+        for d in student_dirs:
+            work, info = self.collect_student_faces(d)
+            window.append((d, work, info))
+            queued += len(work["crops"]) if work is not None else 0
+            if queued >= self.window_crops:
+                flush()
+        flush()
         self.gallery.save()
         stats = self.gallery.get_statistics()
         self._say(f"Total students processed: {len(student_dirs)}  enrolled: {successful}  failed: {failed}")

@@ -22,33 +22,39 @@ def test_config1_match_single_face_loop(tmp_path):
     sd = ob.random_state_dict("ir_50", "adaface", seed=0)
     orc = oe.OracleEmbedder("ir_50", "adaface", state_dict=sd)
     enrolled = _crops(rng, 40)
-    probes = enrolled[:24] + _crops(rng, 8)                      # 24 genuine + 8 impostors = 32 crops
-    # gallery of 100 identities built from ORACLE embeddings: 40 enrolled faces + 60 random unit vectors
-    E = orc.extract_embeddings_batch(enrolled)
-    R = rng.standard_normal((60, 512)).astype(np.float32)
+    impostors = _crops(rng, 8)
+    probes = enrolled[:24] + impostors                           # 24 genuine + 8 impostors = 32 crops
+    # Gallery of 100 identities built from ORACLE embeddings: the 40 enrolled faces, 8 LOOK-ALIKES (each impostor crop
+    # blended half and half with an unrelated crop: scores ~0.80-0.84 against its impostor, everything else <= 0.70)
+    # and 52 random unit vectors.  Every probe's top-1 identity is therefore well-posed - genuine probes by a margin
+    # of ~0.3, impostors by >= 0.1 to their look-alike - and the north star's "top-1 identity 100 % identical" is
+    # asserted for ALL 32 probes, not only the genuine ones (round 1 could only assert it where the margin allowed:
+    # random-init nets map unrelated noise crops to near-equidistant embeddings).
+    r2 = np.random.default_rng(123)
+    lookalikes = [np.clip(0.5 * a.astype(np.float32) + 0.5 * b.astype(np.float32), 0, 255).astype(np.uint8)
+                  for a, b in zip(impostors, _crops(r2, 8))]
+    E = orc.extract_embeddings_batch(enrolled + lookalikes)
+    R = rng.standard_normal((52, 512)).astype(np.float32)
     R /= np.linalg.norm(R, axis=1, keepdims=True)
     G = np.vstack([E, R]).astype(np.float32)
     gm = GalleryManager(gallery_path=str(tmp_path / "students.pkl"))
     for i, row in enumerate(G):
         gm.add_student(f"STU{i:04d}", f"Student {i}", row)
     gm.save()
-    thr = 0.85   # genuine probes score ~1.0, impostors (other noise crops) ~0.6-0.72 with random-init weights
+    thr = 0.9    # genuine probes score ~1.0, impostors ~0.80-0.84 (their look-alike) with random-init weights
     fm = FaceMatcher(gallery_path=str(tmp_path / "students.pkl"), similarity_threshold=thr, architecture="ir_50",
                      embedder=FaceEmbedder("ir_50", state_dict=sd))
     ref_emb = orc.extract_embeddings_batch(probes)
     eidx, esc = og.search_batch(G, ref_emb, 5)
-    # accept/reject must be well-posed for every probe; top-1 identity for every probe whose oracle margin
-    # (top-1 minus top-2) exceeds the embedding tolerance — random-init nets map unrelated noise crops to
-    # near-equidistant embeddings, so impostors' "identity" is decided by margins of ~1e-3 and is ill-posed.
     margin = esc[:, 0] - esc[:, 1]
-    well_posed = margin > 0.02
-    assert well_posed[:24].all()
+    assert (margin > 0.05).all(), margin                         # well-posed for every probe, impostors included
+    assert (eidx[24:, 0] == 40 + np.arange(8)).all()             # an impostor's nearest identity is its look-alike
     assert np.abs(esc[:, 0] - thr).min() > 0.05
+    well_posed = np.ones(len(probes), bool)
     for p, crop in enumerate(probes):
         res = fm.match_single_face(crop, top_k=5)
-        if well_posed[p]:
-            assert res[0][0] == f"STU{eidx[p, 0]:04d}"                              # top-1 identity
-            assert res[0][1] == f"Student {eidx[p, 0]}"
+        assert res[0][0] == f"STU{eidx[p, 0]:04d}"                                  # top-1 identity, all 32 probes
+        assert res[0][1] == f"Student {eidx[p, 0]}"
         assert (res[0][2] >= thr) == (esc[p, 0] >= thr)                             # accept / reject
         assert abs(res[0][2] - esc[p, 0]) < 5e-3 and isinstance(res[0][2], float)
     batch, accept = fm.match_faces_batch(probes, top_k=5)
