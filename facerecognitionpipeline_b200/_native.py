@@ -74,6 +74,7 @@ SIGNATURES = {
     "frb_backbone_load": (_i, [_vp, C.POINTER(LayerDesc), _i, _vp, C.c_size_t, _i]),
     "frb_embed": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "frb_backbone_flops_per_face": (C.c_double, [_vp]),
+    "frb_embed_schedule": (_i, [_vp, _vp]),
     "frb_gallery_upload": (_i, [_vp, _vp, _ll, _ll, _i]),
     "frb_gallery_size": (_ll, [_vp]),
     "frb_gallery_generation": (_ll, [_vp]),

@@ -51,6 +51,20 @@ struct Plan {  // per-batch-size launch plan of the backbone
   std::vector<int> wait_target;    // dataflow: progress units every image must have before this layer may read it
 };
 
+// The FRONT of the network (stem + the 112x112 / 56x56 layers, Cout = 64) run in SUB-BATCHES: for `sub` images at a time
+// the front's layers are launched back to back, so the 1.6 MB-per-image activations a layer writes are still in the
+// 126 MB L2 when the next layer reads them (at 256 images per pass every one of these layers streams 200-800 MB through
+// HBM and runs at about half its speed, profiles/r01e).  Only the front's last output (56x56x64) is kept for the
+// whole batch.  Same kernels, same per-tile instruction streams: no bit changes.
+struct FrontPlan {
+  int B = 0, sub = 0, n_sub = 0, nf = 0;   // batch, images per sub-batch, sub-batches, layers [0, nf)
+  std::vector<int> c0;                      // first image of every sub-batch (the last one is right-aligned)
+  std::vector<int> use_slab, block_n, grid, slab_smem;   // per layer
+  std::vector<std::vector<CUtensorMap>> tmA, tmA2, tmB;  // [sub-batch][layer]
+  std::vector<std::vector<GemmParams>> gp;
+  std::vector<std::vector<SlabParams>> sp;
+};
+
 }  // namespace
 
 struct frb_ctx {
@@ -103,6 +117,11 @@ struct frb_ctx {
   float* d_emb2 = nullptr;  // flip fusion scratch [2B][512]
   size_t emb2_elems = 0;
   Plan plan;
+  FrontPlan front;
+  int front_sub = 0;    // images per front sub-batch (FRB_FRONT_SUB=32 ...; 0 = the front runs with the whole pass like the rest).
+                        // MEASURED slower on (embed 5.70-5.86 ms at 32, 5.53 at 64, 5.96 at 16 vs 5.37-5.44 ms off): the
+                        // per-launch fixed costs of 8 x 7 small launches outweigh the L2 residency they buy.
+  std::vector<int> prof_marks;   // frb_embed_profile: the layer every recorded event precedes
   double flops_per_face = 0.0;
   bool profiling = false;               // frb_embed_profile: CUDA events around every layer launch
   std::vector<cudaEvent_t> prof_events;
@@ -127,6 +146,7 @@ struct frb_ctx {
   int* d_cand_idx = nullptr;
   int* d_flagged = nullptr;
   int* d_flag_rows = nullptr;
+  unsigned* d_row_floor = nullptr;   // [match_cap_P] shared admission floors of the filter (zeroed per match)
   double* d_exact = nullptr;
   size_t exact_elems = 0;
   int match_cap_P = 0, match_cap_slices = 0;
@@ -758,6 +778,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_TAIL_SPLIT")) ctx->tail_split = atoi(e);
   if (const char* e = getenv("FRB_PDL")) ctx->use_pdl = atoi(e);
   if (const char* e = getenv("FRB_EMBED_CHUNK")) ctx->embed_chunk = atoi(e);
+  if (const char* e = getenv("FRB_FRONT_SUB")) ctx->front_sub = atoi(e);
   if (const char* e = getenv("FRB_DATAFLOW")) ctx->use_dataflow = atoi(e);
   if (const char* e = getenv("FRB_MATCH_PAIR")) ctx->match_pair = atoi(e);
   if (!ctx->use_pdl) ctx->use_dataflow = 0;
@@ -823,7 +844,7 @@ extern "C" void frb_ctx_destroy(frb_ctx* ctx) {
   cudaDeviceSynchronize();
   void* ptrs[] = {ctx->d_lut, ctx->d_wtab, ctx->d_blob, ctx->d_fc_partial, ctx->d_emb2, ctx->d_gal, ctx->d_gal_bf16,
                   ctx->d_gal_maxnorm, ctx->d_probe_f32, ctx->d_probe_bf16, ctx->d_cand_score, ctx->d_cand_idx,
-                  ctx->d_flagged, ctx->d_flag_rows, ctx->d_exact, ctx->d_scores64_tmp, ctx->d_stage_u8, ctx->prefetch[0].d_buf, ctx->prefetch[1].d_buf,
+                  ctx->d_flagged, ctx->d_flag_rows, ctx->d_row_floor, ctx->d_exact, ctx->d_scores64_tmp, ctx->d_stage_u8, ctx->prefetch[0].d_buf, ctx->prefetch[1].d_buf,
                   ctx->d_stage_in, ctx->d_stage_emb, ctx->d_stage_norm, ctx->d_stage_sc, ctx->d_stage_idx,
                   ctx->d_stage_acc, ctx->d_jobs, ctx->d_progress, ctx->d_seg, ctx->d_sample_identity, ctx->d_id_top_idx,
                   ctx->d_id_top_sc, ctx->d_id_acc, ctx->d_id_sc32, ctx->d_id_scores, ctx->d_tail_partial, ctx->d_tail_flags, ctx->d_runs, ctx->d_run_bar, ctx->d_sruns};
@@ -1027,6 +1048,16 @@ extern "C" int frb_backbone_load(frb_ctx* ctx, const frb_layer_desc* layers, int
 }
 
 extern "C" double frb_backbone_flops_per_face(frb_ctx* ctx) { return ctx ? ctx->flops_per_face : 0.0; }
+// schedule of the last embed on this ctx: out4 = {faces per pass (chunk), front layers, images per front sub-batch, sub-batches}
+extern "C" int frb_embed_schedule(frb_ctx* ctx, int* out4) {
+  if (!ctx || !out4) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  out4[0] = ctx->plan.B;
+  out4[1] = ctx->front.nf;
+  out4[2] = ctx->front.nf > 0 ? ctx->front.sub : 0;
+  out4[3] = ctx->front.nf > 0 ? ctx->front.n_sub : 0;
+  return 0;
+}
 
 namespace {
 
@@ -1250,6 +1281,96 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
   return 0;
 }
 
+int launch_stem(frb_ctx* ctx, const frb_layer_desc& L, const CUtensorMap& tm_out, const void* in, int B, int* progress, cudaStream_t st) {
+  const uint8_t* blob = ctx->d_blob;
+  if (set_smem_attr(ctx, reinterpret_cast<const void*>(stem_tc_kernel), kStemSmemBytes)) return 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * (L.hin / kStemRows));
+  cfg.blockDim = dim3(kStemThreads);
+  cfg.dynamicSmemBytes = kStemSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  fill_launch_attrs(attr, 1);
+  cfg.attrs = attr + 1;
+  cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+  CK(cudaLaunchKernelEx(&cfg, stem_tc_kernel, tm_out, reinterpret_cast<const __nv_bfloat16*>(in),
+                        reinterpret_cast<const __nv_bfloat16*>(blob + L.w_off), reinterpret_cast<const float*>(blob + L.bias_off),
+                        reinterpret_cast<const float*>(blob + L.prelu_off), static_cast<int>(L.hin), static_cast<int>(L.win), progress));
+  ctx->launches++;
+  return 0;
+}
+
+// How many leading layers form the front: stem + conv layers on >= 56-pixel inputs with Cout <= 64, provided the buffer
+// the front ends in is used with ONE per-image size inside the front (it is addressed at the sub-batch's image offset).
+int front_layers(const frb_ctx* ctx) {
+  const auto& Ls = ctx->layers;
+  size_t nf = 0;
+  while (nf < Ls.size() && (Ls[nf].op == FRB_OP_STEM || (Ls[nf].op == FRB_OP_CONV && Ls[nf].hin >= 56 && Ls[nf].cout <= 64))) ++nf;
+  if (nf < 2 || nf >= Ls.size() || Ls[0].op != FRB_OP_STEM) return 0;
+  const int ext = Ls[nf - 1].out_buf;
+  const auto& F = Ls[nf - 1];
+  const long long want = static_cast<long long>(out_dim(F.hin, F.ksize, F.stride, F.pad)) * out_dim(F.win, F.ksize, F.stride, F.pad) * F.cout;
+  for (size_t i = 0; i < nf; ++i) {
+    const auto& L = Ls[i];
+    const long long out_e = static_cast<long long>(out_dim(L.hin, L.ksize, L.stride, L.pad)) * out_dim(L.win, L.ksize, L.stride, L.pad) * L.cout;
+    if (L.out_buf == ext && out_e != want) return 0;
+    if (L.in_buf == ext && static_cast<long long>(L.hin) * L.win * L.cin != want) return 0;
+    if (L.sc_buf == ext && static_cast<long long>(L.sc_hin) * L.sc_win * L.sc_cin != want) return 0;
+    if (L.res_buf == ext && static_cast<long long>(L.res_h) * L.res_w * L.cout != want) return 0;
+  }
+  return static_cast<int>(nf);
+}
+
+int build_front(frb_ctx* ctx, int B) {
+  FrontPlan& fp = ctx->front;
+  fp = FrontPlan();
+  const int nf = front_layers(ctx);
+  if (nf == 0 || ctx->front_sub <= 0 || B <= ctx->front_sub || ctx->conv_mode != 2) return 0;   // fp.nf == 0: no front
+  fp.B = B; fp.nf = nf;
+  fp.n_sub = (B + ctx->front_sub - 1) / ctx->front_sub;
+  fp.sub = (B + fp.n_sub - 1) / fp.n_sub;
+  const int ext = ctx->layers[nf - 1].out_buf;
+  fp.use_slab.assign(nf, 0); fp.block_n.assign(nf, 0); fp.grid.assign(nf, 0); fp.slab_smem.assign(nf, 0);
+  fp.tmA.assign(fp.n_sub, std::vector<CUtensorMap>(nf)); fp.tmA2 = fp.tmA; fp.tmB = fp.tmA;
+  fp.gp.assign(fp.n_sub, std::vector<GemmParams>(nf)); fp.sp.assign(fp.n_sub, std::vector<SlabParams>(nf));
+  const uint8_t* blob = ctx->d_blob;
+  for (int c = 0; c < fp.n_sub; ++c) {
+    const int c0 = std::min(c * fp.sub, B - fp.sub);
+    fp.c0.push_back(c0);
+    // buffer `id` as this sub-batch sees it: the front's final buffer at the sub-batch's images, everything else from 0
+    auto buf = [&](int id, long long per_image) -> __nv_bfloat16* {
+      if (id < 0) return nullptr;
+      return ctx->d_bufs[id] + (id == ext ? static_cast<size_t>(c0) * per_image : 0);
+    };
+    for (int i = 0; i < nf; ++i) {
+      const frb_layer_desc& L = ctx->layers[i];
+      const long long out_e = static_cast<long long>(out_dim(L.hin, L.ksize, L.stride, L.pad)) * out_dim(L.win, L.ksize, L.stride, L.pad) * L.cout;
+      __nv_bfloat16* out = buf(L.out_buf, out_e);
+      if (L.op == FRB_OP_STEM) {
+        if (make_tmap_2d(ctx, &fp.tmA[c][i], out, 64, static_cast<uint64_t>(fp.sub) * L.hin * L.win, L.win)) return 1;
+        continue;
+      }
+      const void* in = buf(L.in_buf, static_cast<long long>(L.hin) * L.win * L.cin);
+      const void* sc = buf(L.sc_buf, static_cast<long long>(L.sc_hin) * L.sc_win * L.sc_cin);
+      const void* res = buf(L.res_buf, static_cast<long long>(L.res_h) * L.res_w * L.cout);
+      const float* bias = reinterpret_cast<const float*>(blob + L.bias_off);
+      const float* prelu = reinterpret_cast<const float*>(blob + L.prelu_off);
+      if (slab_eligible(ctx, L, sc != nullptr)) {
+        fp.use_slab[i] = 1;
+        if (setup_slab(ctx, L, fp.sub, in, res, blob + L.w_off, bias, prelu, out, &fp.tmA[c][i], &fp.tmB[c][i], &fp.sp[c][i],
+                       &fp.slab_smem[i], &fp.grid[i]))
+          return 1;
+      } else {
+        if (setup_conv(ctx, L, fp.sub, in, sc, res, blob + L.w_off, bias, prelu, out, &fp.tmA[c][i], &fp.tmA2[c][i], &fp.tmB[c][i],
+                       &fp.gp[c][i], &fp.block_n[i], &fp.grid[i]))
+          return 1;
+        if (fp.gp[c][i].tail_split > 1 || fp.gp[c][i].quad) { fp = FrontPlan(); return 0; }   // experiments only: no front then
+      }
+    }
+  }
+  return 0;
+}
+
 // Bn faces through the network in ONE pass of the layer program (no flip pairing here: l2 / renorm as given).
 int embed_chunk_locked(frb_ctx* ctx, const void* d_in, int Bn, int l2, int renorm, float* d_emb, float* d_norm,
                        void* d_emb_bf16, cudaStream_t st) {
@@ -1260,26 +1381,47 @@ int embed_chunk_locked(frb_ctx* ctx, const void* d_in, int Bn, int l2, int renor
     if (build_plan(ctx, Bn, d_in)) return 1;
     ctx->plan.d_in = d_in;
     ctx->plan.dataflow = want_df;
+    ctx->front = FrontPlan();
+    if (!want_df && build_front(ctx, Bn)) return 1;
   }
   Plan& pl = ctx->plan;
+  const FrontPlan& fp = ctx->front;
+  const size_t face_bytes = static_cast<size_t>(112) * 112 * 3 * 2;
   const bool dataflow = pl.dataflow && ctx->conv_mode == 2;
   if (dataflow) CK(cudaMemsetAsync(ctx->d_progress, 0, sizeof(int) * Bn, st));
   if (pl.tail_flags > 0) CK(cudaMemsetAsync(ctx->d_tail_flags, 0, sizeof(int) * pl.tail_flags, st));
   if (pl.num_runs > 0) CK(cudaMemsetAsync(ctx->d_run_bar, 0, sizeof(int) * pl.run_layers, st));
   size_t run_end = 0;  // layers below this index were covered by a persistent run launch
-  if (ctx->profiling) {
-    while (ctx->prof_events.size() < ctx->layers.size() + 1) {
+  // frb_embed_profile: an event before every launch, tagged with its layer (a front layer is launched once per sub-batch)
+  ctx->prof_marks.clear();
+  auto mark = [&](int layer) -> int {
+    if (!ctx->profiling) return 0;
+    const size_t k = ctx->prof_marks.size();
+    while (ctx->prof_events.size() <= k) {
       cudaEvent_t e;
       CK(cudaEventCreate(&e));
       ctx->prof_events.push_back(e);
     }
-    CK(cudaEventRecord(ctx->prof_events[0], st));
-  }
-  for (size_t i = 0; i < ctx->layers.size(); ++i) {
+    CK(cudaEventRecord(ctx->prof_events[k], st));
+    ctx->prof_marks.push_back(layer);
+    return 0;
+  };
+  // ---- the front, sub-batch by sub-batch
+  for (int c = 0; c < (fp.nf > 0 ? fp.n_sub : 0); ++c)
+    for (int i = 0; i < fp.nf; ++i) {
+      const frb_layer_desc& L = ctx->layers[i];
+      if (mark(i)) return 1;
+      if (L.op == FRB_OP_STEM) {
+        if (launch_stem(ctx, L, fp.tmA[c][i], static_cast<const uint8_t*>(d_in) + fp.c0[c] * face_bytes, fp.sub, nullptr, st)) return 1;
+      } else if (fp.use_slab[i]) {
+        if (launch_slab(ctx, L.cin / 64, fp.tmA[c][i], fp.tmB[c][i], fp.sp[c][i], fp.slab_smem[i], fp.grid[i], st)) return 1;
+      } else if (launch_conv(ctx, fp.block_n[i], fp.tmA[c][i], fp.tmA2[c][i], fp.tmB[c][i], fp.gp[c][i], fp.grid[i], st)) return 1;
+    }
+  for (size_t i = static_cast<size_t>(fp.nf); i < ctx->layers.size(); ++i) {
     const frb_layer_desc& L = ctx->layers[i];
     const uint8_t* blob = ctx->d_blob;
-    if (ctx->profiling && i > 0) CK(cudaEventRecord(ctx->prof_events[i], st));
     if (i < run_end) continue;
+    if (mark(static_cast<int>(i))) return 1;
     if (pl.srun_len[i] > 1) {
       CK(cudaMemsetAsync(ctx->d_progress, 0, sizeof(int) * Bn, st));  // run-local progress
       if (launch_slab_multi(ctx, L.cin / 64, L.cout, ctx->d_sruns + pl.srun_off[i], pl.srun_len[i], pl.slab_smem[i], pl.grid[i], st))
@@ -1297,22 +1439,7 @@ int embed_chunk_locked(frb_ctx* ctx, const void* d_in, int Bn, int l2, int renor
     }
     if (L.op == FRB_OP_STEM) {
       const void* in = L.in_buf < 0 ? d_in : ctx->d_bufs[L.in_buf];
-      if (set_smem_attr(ctx, reinterpret_cast<const void*>(stem_tc_kernel), kStemSmemBytes)) return 1;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(Bn * (L.hin / kStemRows));
-      cfg.blockDim = dim3(kStemThreads);
-      cfg.dynamicSmemBytes = kStemSmemBytes;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[2];
-      fill_launch_attrs(attr, 1);
-      cfg.attrs = attr + 1;
-      cfg.numAttrs = ctx->use_pdl ? 1 : 0;
-      CK(cudaLaunchKernelEx(&cfg, stem_tc_kernel, pl.tmA[i], reinterpret_cast<const __nv_bfloat16*>(in),
-                            reinterpret_cast<const __nv_bfloat16*>(blob + L.w_off), reinterpret_cast<const float*>(blob + L.bias_off),
-                            reinterpret_cast<const float*>(blob + L.prelu_off), static_cast<int>(L.hin), static_cast<int>(L.win),
-                            dataflow ? ctx->d_progress : static_cast<int*>(nullptr)));
-      CK(cudaGetLastError());
-      ctx->launches++;
+      if (launch_stem(ctx, L, pl.tmA[i], in, Bn, dataflow ? ctx->d_progress : static_cast<int*>(nullptr), st)) return 1;
     } else if (L.op == FRB_OP_CONV) {
       if (pl.use_slab[i]) {
         if (launch_slab(ctx, L.cin / 64, pl.tmA[i], pl.tmB[i], pl.sp[i], pl.slab_smem[i], pl.grid[i], st)) return 1;
@@ -1326,7 +1453,7 @@ int embed_chunk_locked(frb_ctx* ctx, const void* d_in, int Bn, int l2, int renor
       ctx->launches++;
     }
   }
-  if (ctx->profiling) CK(cudaEventRecord(ctx->prof_events[ctx->layers.size()], st));
+  if (mark(-1)) return 1;   // closing event
   return 0;
 }
 
@@ -1396,11 +1523,15 @@ extern "C" int frb_embed_profile(frb_ctx* ctx, const void* d_in, int B, int flag
   const int nl = static_cast<int>(ctx->layers.size());
   const int Bn = (flags & FRB_EMBED_FLIP) ? 2 * B : B;
   if (n_layers) *n_layers = nl;
+  std::vector<float> layer_ms(nl, 0.f);
+  for (size_t k = 0; k + 1 < ctx->prof_marks.size(); ++k) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->prof_events[k], ctx->prof_events[k + 1]));
+    if (ctx->prof_marks[k] >= 0 && ctx->prof_marks[k] < nl) layer_ms[ctx->prof_marks[k]] += ms;
+  }
   for (int i = 0; i < nl && i < max_layers; ++i) {
     const frb_layer_desc& L = ctx->layers[i];
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
-    if (h_layer_ms) h_layer_ms[i] = ms;
+    if (h_layer_ms) h_layer_ms[i] = layer_ms[i];
     int id = 7;
     if (L.op == FRB_OP_STEM) id = 0;
     else if (L.op == FRB_OP_CONV) {
@@ -1608,15 +1739,18 @@ int match_workspace(frb_ctx* ctx, int P) {
     if (ctx->d_probe_bf16) CK(cudaFree(ctx->d_probe_bf16));
     if (ctx->d_flagged) CK(cudaFree(ctx->d_flagged));
     if (ctx->d_flag_rows) CK(cudaFree(ctx->d_flag_rows));
+    if (ctx->d_row_floor) CK(cudaFree(ctx->d_row_floor));
     if (ctx->d_cand_score) CK(cudaFree(ctx->d_cand_score));
     if (ctx->d_cand_idx) CK(cudaFree(ctx->d_cand_idx));
     ctx->d_probe_f32 = nullptr; ctx->d_probe_bf16 = nullptr; ctx->d_flagged = nullptr; ctx->d_flag_rows = nullptr;
+    ctx->d_row_floor = nullptr;
     ctx->d_cand_score = nullptr; ctx->d_cand_idx = nullptr; ctx->match_cap_slices = 0;
     const int cap = std::max(P, 128);
     CK(cudaMalloc(&ctx->d_probe_f32, static_cast<size_t>(cap) * 512 * 4));
     CK(cudaMalloc(&ctx->d_probe_bf16, static_cast<size_t>(cap) * 512 * 2));
     CK(cudaMalloc(&ctx->d_flagged, static_cast<size_t>(cap) * 4));
     CK(cudaMalloc(&ctx->d_flag_rows, static_cast<size_t>(cap) * 4));
+    CK(cudaMalloc(&ctx->d_row_floor, static_cast<size_t>(cap) * 4));
     ctx->match_cap_P = cap;
   }
   return 0;
@@ -1693,6 +1827,7 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
   if (ensure(ctx, &ctx->d_exact_part, &ctx->exact_part_cap, static_cast<size_t>(P) * kExactBlocks * k)) return 1;
   mp.cand_score = ctx->d_cand_score;
   mp.cand_idx = ctx->d_cand_idx;
+  mp.row_floor = ctx->d_row_floor;
   CUtensorMap tmP;
   if (make_tmap_2d(ctx, &tmP, d_probe_bf16, 512, static_cast<uint64_t>(P), 128)) return 1;
   if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[1], st));
@@ -1758,6 +1893,7 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
   double* s64 = d_scores64;
   if (!s64 && scores64_scratch(ctx, static_cast<size_t>(P) * k, &s64)) return 1;
   CK(cudaMemsetAsync(ctx->d_match_ctr, 0, 8, st));   // device counters of this match: flagged rows, rows pushed
+  CK(cudaMemsetAsync(ctx->d_row_floor, 0, static_cast<size_t>(P) * 4, st));   // the filter's shared admission floors
   if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[0], st));
   probe_prepare_kernel<<<P, 128, 0, st>>>(d_probes, normalize, ctx->d_probe_f32, ctx->d_probe_bf16);
   CK(cudaGetLastError());
@@ -2149,6 +2285,7 @@ extern "C" int frb_match_sharded(frb_ctx* ctx, const float* d_local_probes, int 
   const unsigned epoch = ++x.epoch;
   const int G = x.world;
   CK(cudaMemsetAsync(ctx->d_match_ctr, 0, 12, st));   // flagged rows, rows pushed, probe rows pushed
+  CK(cudaMemsetAsync(ctx->d_row_floor, 0, static_cast<size_t>(P_total) * 4, st));
   // 1. probes -> everyone
   ProbePush pq;
   memset(&pq, 0, sizeof(pq));

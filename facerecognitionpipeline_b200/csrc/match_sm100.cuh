@@ -47,7 +47,19 @@ struct MatchParams {
   int tiles_per_slice;   // ceil(g_tiles / slices)
   float* cand_score;     // [P][slices][kCand]
   int* cand_idx;         // [P][slices][kCand]  (local gallery row, -1 = empty)
+  unsigned* row_floor;   // [P] shared admission floors (ordered-integer image of a score, 0 = none yet), zeroed per match
 };
+
+// Order-preserving image of a float in an unsigned integer (so atomicMax works on scores of either sign); 0 is below
+// every real score.
+__device__ __forceinline__ unsigned score_key(float v) {
+  const unsigned b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_score(unsigned k) {
+  if (k == 0u) return -INFINITY;
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 
 struct MatchSmem {
   static constexpr int kABytes = 128 * 64 * 2;       // one K block of the probe tile (16 KB)
@@ -74,11 +86,16 @@ __device__ __forceinline__ void cand_insert(float (&ls)[kCand], int (&li)[kCand]
 // instructions, not 32 predicated insertions (~1300): with 32 independent rows per warp SOME lane has a
 // candidate in most chunks until ~10^5 scores have been seen, and that path bounded the whole match
 // (profiles/r01c: tensor pipe 37 % active at P = 4096).
-__device__ __forceinline__ void cand_scan32(float (&ls)[kCand], int (&li)[kCand], float (&v)[32], int base) {
+// `floor`: admission floor shared by all slices of the probe row (see MatchParams::row_floor): scores not above it are
+// dropped without touching the list.  It never exceeds the smallest kept score of some FULL slice list, so the bound
+// match_finalize_kernel derives from the full lists (max over slices of their last entry) already covers every
+// element dropped this way - the proof there is unchanged.
+__device__ __forceinline__ void cand_scan32(float (&ls)[kCand], int (&li)[kCand], float (&v)[32], int base, float floor) {
   float m = v[0];
 #pragma unroll
   for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-  if (!(m > ls[kCand - 1])) return;
+  const float gate = fmaxf(ls[kCand - 1], floor);
+  if (!(m > gate)) return;
 #pragma unroll 1
   while (true) {
     float best = v[0];
@@ -89,12 +106,30 @@ __device__ __forceinline__ void cand_scan32(float (&ls)[kCand], int (&li)[kCand]
         best = v[j];
         bj = j;
       }
-    if (!(best > ls[kCand - 1])) break;
+    if (!(best > fmaxf(ls[kCand - 1], floor))) break;
     cand_insert(ls, li, best, base + bj);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j == bj) v[j] = -INFINITY;
   }
+}
+
+// Slices of one probe row warm each other up: a thread whose list is full publishes its smallest kept score
+// (atomicMax on the ordered-integer image) and, once per gallery tile, takes the largest value published so far as
+// its floor.  With 37-74 slices per probe tile running at once the floors reach the level of the row's few-hundredth
+// best score after a tile or two, instead of every slice refilling a cold list through the slow insertion path
+// (the limiter named in profiles/r01c: tensor pipe 37 % active at P = 4096 while the lists were cold).
+__device__ __forceinline__ float floor_exchange(unsigned* row_floor, int row, bool row_ok, const float (&ls)[kCand],
+                                                const int (&li)[kCand], unsigned& published) {
+  if (!row_ok) return -INFINITY;
+  if (li[kCand - 1] >= 0) {   // full list: its last entry bounds everything this slice dropped or will drop
+    const unsigned mine = score_key(ls[kCand - 1]);
+    if (mine > published) {
+      atomicMax(row_floor + row, mine);
+      published = mine;
+    }
+  }
+  return key_score(__ldcg(row_floor + row));
 }
 
 __global__ void __launch_bounds__(kMatchThreads, 1)
@@ -247,7 +282,9 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
         ls[i] = -INFINITY;
         li[i] = -1;
       }
+      unsigned published = 0u;
       for (int t = t_begin; t < t_end; ++t) {
+        const float floor = floor_exchange(p.row_floor, row, row < p.P, ls, li, published);
         mbar_wait(&t_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kMatchBN;
@@ -268,7 +305,7 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
             for (int j = 0; j < 32; ++j)
               v[j] = (c * 32 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY;
           }
-          cand_scan32(ls, li, v, static_cast<int>(col0) + c * 32);
+          cand_scan32(ls, li, v, static_cast<int>(col0) + c * 32, floor);
         }
         tc_fence_before();
         __syncwarp();
@@ -278,6 +315,7 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
           acc_phase ^= 1;
         }
       }
+      (void)floor_exchange(p.row_floor, row, row < p.P, ls, li, published);   // the final list helps the slices still running
       if (row < p.P) {
         const size_t o = (static_cast<size_t>(row) * p.slices + gs) * kCand;
         float4* ds = reinterpret_cast<float4*>(p.cand_score + o);
@@ -473,7 +511,9 @@ match_filter2_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
         ls[i] = -INFINITY;
         li[i] = -1;
       }
+      unsigned published = 0u;
       for (int t = t_begin; t < t_end; ++t) {
+        const float floor = floor_exchange(p.row_floor, row, row < p.P, ls, li, published);
         mbar_wait(&t_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kMatchBN;
@@ -493,7 +533,7 @@ match_filter2_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (c * 32 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY;
           }
-          cand_scan32(ls, li, v, static_cast<int>(col0) + c * 32);
+          cand_scan32(ls, li, v, static_cast<int>(col0) + c * 32, floor);
         }
         tc_fence_before();
         __syncwarp();
@@ -503,6 +543,7 @@ match_filter2_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
           acc_phase ^= 1;
         }
       }
+      (void)floor_exchange(p.row_floor, row, row < p.P, ls, li, published);   // the final list helps the slices still running
       if (row < p.P) {
         const size_t o = (static_cast<size_t>(row) * p.slices + gs) * kCand;
         float4* ds = reinterpret_cast<float4*>(p.cand_score + o);

@@ -87,6 +87,10 @@ int frb_backbone_load(frb_ctx* ctx, const frb_layer_desc* layers, int n_layers, 
 int frb_embed(frb_ctx* ctx, const void* d_in, int B, int flags, float* d_emb, float* d_norm,
               void* d_emb_bf16, void* stream);
 double frb_backbone_flops_per_face(frb_ctx* ctx);
+/* schedule of the last embed: out4 = {faces per pass of the layer program (large batches are chunked, default 256),
+ * number of leading "front" layers run in sub-batches (stem + the 112/56-pixel Cout-64 layers), images per sub-batch
+ * (default 32: their activations then stay in L2 between layers), sub-batches per pass}.  FRB_EMBED_CHUNK / FRB_FRONT_SUB. */
+int frb_embed_schedule(frb_ctx* ctx, int* out4);
 /* measurement aid (bench.py roofline): frb_embed with a CUDA event between consecutive layers; per layer the
  * duration (ms), the kernel that ran it (0 stem, 1/2/3 CTA-pair im2col conv with Cout tile 64/128/256,
  * 4/5/6 slab conv <64,1>/<128,1>/<128,2>, 7 FC + finalize) and its FLOPs for this batch. */

@@ -136,7 +136,9 @@ def test_launch_schedules_are_bit_identical(tmp_path):
     per-image dataflow between its layers, FRB_MULTI=2), the same run with grid barriers (FRB_MULTI=1), one launch
     per layer with programmatic dependent launch (FRB_MULTI=0), plain stream order (FRB_PDL=0) and per-image dataflow
     across launches (FRB_DATAFLOW=1) — must produce bit-identical embeddings: they only change WHEN a tile runs,
-    never what it computes."""
+    never what it computes.  Round 2 adds: the front (stem + 112/56-pixel layers) in sub-batches of 32 images (default),
+    without them (FRB_FRONT_SUB=0), with a right-aligned overlapping last sub-batch (150 faces in 4 x 38), the pass cut
+    into chunks of 64 faces (FRB_EMBED_CHUNK), and the persistent slab run with the streamed weight swap."""
     import os
     import subprocess
     import sys
@@ -154,7 +156,9 @@ def test_launch_schedules_are_bit_identical(tmp_path):
     outs = []
     for name, env in (("plain", {"FRB_PDL": "0", "FRB_MULTI": "0"}), ("pdl", {"FRB_MULTI": "0"}), ("default", {}),
                       ("run_barrier", {"FRB_MULTI": "1"}), ("run_flow_plain", {"FRB_MULTI": "2", "FRB_PDL": "0"}),
-                      ("dataflow", {"FRB_DATAFLOW": "1"})):
+                      ("dataflow", {"FRB_DATAFLOW": "1"}), ("no_front", {"FRB_FRONT_SUB": "0"}),
+                      ("front_overlap", {"FRB_FRONT_SUB": "40"}), ("chunk_64", {"FRB_EMBED_CHUNK": "64"}),
+                      ("slab_run", {"FRB_SLAB_MULTI": "1"})):
         out = tmp_path / f"{name}.npy"
         subprocess.run([sys.executable, str(script), str(out)], check=True, env={**os.environ, **env}, timeout=600)
         outs.append(np.load(out))

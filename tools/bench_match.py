@@ -25,3 +25,22 @@ for P in [int(a) for a in sys.argv[1:]] or [256, 1024, 4096]:
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 10
     print(f"P={P:5d} N={N}: {ms:8.3f} ms  {P*1024.0*N/ms/1e9:7.1f} TFLOP/s  gallery pass {N*1024/ms/1e6:7.1f} GB/s-equivalent  flagged {ctx._lib.frb_match_last_flagged(ctx.handle)}", flush=True)
+    ms3 = (C.c_float * 3)()
+    parts = []
+    for _ in range(3):
+        ctx.frb_match_profile(probes.data_ptr(), P, 5, 0.35, 1, sc.data_ptr(), ix.data_ptr(), ac.data_ptr(), st, ms3)
+        parts.append(list(ms3))
+    print("        parts (prepare | filter | finalize + fix-up) ms:", [round(float(x), 4) for x in sorted(parts)[1]], flush=True)
+    if os.environ.get("FRB_SHARDED1", "0") == "1" and P <= 4096:
+        # the sharded entry point with a world of ONE: probe push + flag wait + match + row push + merge on this GPU alone
+        # (what one rank of an N-rank sharded match spends when it never waits for a peer)
+        if not getattr(ctx, "_x", False):
+            ctx.frb_xchg_create(1, 0, 4096, 8, (C.c_ubyte * 64)())
+            ctx._x = True
+        fs = lambda: ctx.frb_match_sharded(probes.data_ptr(), 0, P, P, 5, 0.35, 1, sc.data_ptr(), ix.data_ptr(), ac.data_ptr(), st)
+        for _ in range(3): fs()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(10): fs()
+        b.record(); torch.cuda.synchronize()
+        print(f"        frb_match_sharded, world 1: {a.elapsed_time(b) / 10:8.3f} ms", flush=True)
