@@ -531,6 +531,27 @@ def run_ours(args):
     if c4:
         per_kernel_list.append(hbm_entry("warp_normalize_kernel (1024 faces)", c4["warp"]["algorithmic_bytes"],
                                          c4["warp"]["ms"] * 1e3, 1, "source footprint + 75 264 B written per face (SURVEY 8d)"))
+    # read-only and write-only HBM streams measured here (libfrb200's own probe, 1 GiB, 16-byte accesses): the yardstick for
+    # kernels that only read (match filter) or only write (stem) next to the read+write copy figure of MEASURED_PEAKS.json
+    stream = None
+    try:
+        scratch = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        t_ms = C.c_float(0)
+        ctx.frb_debug_stream_bw(scratch.data_ptr(), scratch.numel(), 0, 5, C.byref(t_ms))
+        rd = scratch.numel() / t_ms.value / 1e6
+        ctx.frb_debug_stream_bw(scratch.data_ptr(), scratch.numel(), 1, 5, C.byref(t_ms))
+        wr = scratch.numel() / t_ms.value / 1e6
+        del scratch
+        stream = dict(read_only_gbs=rd, write_only_gbs=wr, copy_gbs=peaks["hbm"],
+                      note="frb_debug_stream_bw, 1 GiB, measured in this run after the timed region")
+        for e in per_kernel_list:
+            if e.get("bound") == "hbm" and e["kernel"].startswith("match_filter"):
+                e["frac_of_read_only_stream"] = e["achieved"] / rd
+            if e.get("bound") == "hbm" and e["kernel"].startswith("stem"):
+                e["frac_of_write_only_stream"] = e["achieved"] / wr
+    except Exception as ex:   # the probe is informative only
+        stream = dict(error=str(ex)[:200])
+    roofline["stream_peaks"] = stream
     roofline["frac_of_burst"] = dom_tf / peaks["tf_burst"]
     roofline["per_kernel"] = per_kernel_list
     cpu = None

@@ -104,6 +104,7 @@ SIGNATURES = {
     "frb_embed_profile": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "frb_debug_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "frb_debug_conv": (_i, [_vp, C.POINTER(LayerDesc), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "frb_debug_stream_bw": (_i, [_vp, _vp, C.c_size_t, _i, _i, _vp]),
     "frb_debug_shift_mma": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "frb_debug_mma_rate": (_i, [_vp, _i, _i, _i, _vp]),
     "frb_debug_mma2_rate": (_i, [_vp, _i, _i, _i, _vp]),

@@ -1851,6 +1851,7 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
   fp.cand_score = ctx->d_cand_score; fp.cand_idx = ctx->d_cand_idx; fp.slices = mp.slices;
   fp.probes = d_probe_f32; fp.gallery = ctx->d_gal; fp.N = N; fp.first_global_id = ctx->gal_first;
   fp.k = k; fp.thr = thr; fp.max_norm = ctx->d_gal_maxnorm;
+  fp.rescore = std::min(kRescore, std::max(24, 8 * k));
   fp.out_score = s64; fp.out_idx = d_idx; fp.out_score_f32 = d_scores; fp.out_accept = d_accept;
   fp.flagged = ctx->d_flagged; fp.flag_rows = ctx->d_flag_rows; fp.flag_count = ctx->d_match_ctr;
   fp.push = pp;
@@ -1892,10 +1893,10 @@ int match_locked(frb_ctx* ctx, const float* d_probes, int P, int k, float thr, i
   if (match_workspace(ctx, P)) return 1;
   double* s64 = d_scores64;
   if (!s64 && scores64_scratch(ctx, static_cast<size_t>(P) * k, &s64)) return 1;
-  CK(cudaMemsetAsync(ctx->d_match_ctr, 0, 8, st));   // device counters of this match: flagged rows, rows pushed
-  CK(cudaMemsetAsync(ctx->d_row_floor, 0, static_cast<size_t>(P) * 4, st));   // the filter's shared admission floors
   if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[0], st));
-  probe_prepare_kernel<<<P, 128, 0, st>>>(d_probes, normalize, ctx->d_probe_f32, ctx->d_probe_bf16);
+  // the kernel also zeroes this match's device state: its rows' admission floors and the flagged / pushed counters
+  probe_prepare_kernel<<<P, 128, 0, st>>>(d_probes, normalize, ctx->d_probe_f32, ctx->d_probe_bf16, ctx->d_row_floor,
+                                          ctx->d_match_ctr);
   CK(cudaGetLastError());
   ctx->launches++;
   return match_core(ctx, ctx->d_probe_f32, ctx->d_probe_bf16, P, k, thr, d_scores, d_idx, d_accept, s64, nullptr, st);
@@ -2000,7 +2001,7 @@ extern "C" int frb_identity_scores(frb_ctx* ctx, const float* d_probes, int P, i
   if (ws_begin(ctx, st)) return 1;
   float* d_norm = nullptr;
   CK(cudaMallocAsync(reinterpret_cast<void**>(&d_norm), static_cast<size_t>(P) * 512 * 4, st));
-  probe_prepare_kernel<<<P, 128, 0, st>>>(d_probes, normalize, d_norm, nullptr);
+  probe_prepare_kernel<<<P, 128, 0, st>>>(d_probes, normalize, d_norm, nullptr, nullptr, nullptr);
   CK(cudaGetLastError());
   ctx->launches++;
   for (int f0 = 0; f0 < P; f0 += kExactChunk) {
@@ -2594,6 +2595,61 @@ extern "C" int frb_debug_im2col(frb_ctx* ctx, const void* d_in, int B, int H, in
       tm, c0, qq * stride - pad, pp * stride - pad, img, tap_s, tap_r, reinterpret_cast<uint4*>(d_out_16k));
   CK(cudaGetLastError());
   ctx->launches++;
+  return 0;
+}
+
+// ---- probe: read-only / write-only HBM stream (the yardstick for kernels that only read - the match filter's bf16
+// gallery - or only write - the stem's activations; MEASURED_PEAKS.json holds the read+write copy figure).
+namespace {
+__global__ void __launch_bounds__(256) stream_read_kernel(const uint4* __restrict__ p, size_t n16, unsigned* __restrict__ sink) {
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {   // four independent 16-byte loads in flight per thread
+    const uint4 a = __ldcs(p + i), b = __ldcs(p + i + stride), c = __ldcs(p + i + 2 * stride), d = __ldcs(p + i + 3 * stride);
+    acc.x ^= a.x ^ b.x ^ c.x ^ d.x; acc.y ^= a.y ^ b.y ^ c.y ^ d.y; acc.z ^= a.z ^ b.z ^ c.z ^ d.z; acc.w ^= a.w ^ b.w ^ c.w ^ d.w;
+  }
+  for (; i < n16; i += stride) {
+    const uint4 a = __ldcs(p + i);
+    acc.x ^= a.x; acc.y ^= a.y; acc.z ^= a.z; acc.w ^= a.w;
+  }
+  if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) *sink = acc.x;   // practically never: keeps the loads alive
+}
+__global__ void __launch_bounds__(256) stream_write_kernel(uint4* __restrict__ p, size_t n16, unsigned v) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16; i += stride) __stcs(p + i, make_uint4(v, v, v, v));
+}
+}  // namespace
+
+// mode 0: read `bytes` once per iteration, mode 1: write them; h_ms = average duration of one pass (CUDA events)
+extern "C" int frb_debug_stream_bw(frb_ctx* ctx, void* d_buf, size_t bytes, int mode, int iters, float* h_ms) {
+  if (!ctx || !d_buf || !h_ms || iters < 1) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  unsigned* sink = nullptr;
+  CK(cudaMalloc(&sink, 4));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  const size_t n16 = bytes / 16;
+  const int grid = ctx->num_sms * 8;
+  auto pass = [&]() {
+    if (mode == 0) stream_read_kernel<<<grid, 256>>>(reinterpret_cast<const uint4*>(d_buf), n16, sink);
+    else stream_write_kernel<<<grid, 256>>>(reinterpret_cast<uint4*>(d_buf), n16, 0x3c003c00u);
+  };
+  pass();
+  CK(cudaEventRecord(a));
+  for (int i = 0; i < iters; ++i) pass();
+  CK(cudaEventRecord(b));
+  CK(cudaEventSynchronize(b));
+  CK(cudaGetLastError());
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  *h_ms = ms / iters;
+  ctx->launches += iters + 1;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(sink);
   return 0;
 }
 

@@ -861,12 +861,21 @@ aggregate_templates_kernel(const float* __restrict__ emb, const long long* __res
 
 // ------------------------------------------------------------------ probe / gallery prep
 // q = q / (||q|| + 1e-8)  (GalleryManager.search, gallery_manager.py:195), fp32, + bf16 copy
+// row_floor / counters (either may be null): the match's per-call device state is zeroed here - block b its row's
+// admission floor, block 0 the two counters - instead of by memset nodes in front of the kernel.
 __global__ void __launch_bounds__(128)
 probe_prepare_kernel(const float* __restrict__ in, int normalize, float* __restrict__ out_f32,
-                     __nv_bfloat16* __restrict__ out_bf16) {
+                     __nv_bfloat16* __restrict__ out_bf16, unsigned* __restrict__ row_floor, int* __restrict__ counters) {
   const int b = blockIdx.x, t = threadIdx.x;
   __shared__ float red[4];
   pdl_launch_dependents();   // the filter kernel may set itself up (barriers, TMEM, tensor maps) while this runs
+  if (t == 0) {
+    if (row_floor) row_floor[b] = 0u;
+    if (counters && b == 0) {
+      counters[0] = 0;
+      counters[1] = 0;
+    }
+  }
   float x[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) x[j] = in[static_cast<size_t>(b) * 512 + t + 128 * j];
@@ -1007,6 +1016,7 @@ struct FinalizeParams {
   long long N;
   long long first_global_id;
   int k;
+  int rescore;               // survivors re-scored exactly: 8 k clamped to [24, kRescore] (all of them only for k > 8)
   float thr;
   const float* max_norm;     // gallery max row norm (device scalar)
   double* out_score;         // [P][k] f64
@@ -1097,11 +1107,14 @@ match_finalize_kernel(const FinalizeParams p) {
     const int valid = count_ge(1u);
     const int want = valid < 128 ? valid : 128;
     unsigned lo = 1u, hi = 0xFFFFFFFFu;      // largest key threshold that still keeps `want` candidates
-    while (lo < hi) {
-      const unsigned mid = lo + (hi - lo + 1u) / 2u;
-      if (count_ge(mid) >= want) lo = mid; else hi = mid - 1u;
-    }
-    const int kept = count_ge(lo);
+    // (with the filter's shared admission floors most slice lists hold only a few entries: when at most 256 are valid
+    // they are all kept and the 32 counting passes are skipped)
+    if (valid > 256)
+      while (lo < hi) {
+        const unsigned mid = lo + (hi - lo + 1u) / 2u;
+        if (count_ge(mid) >= want) lo = mid; else hi = mid - 1u;
+      }
+    const int kept = valid > 256 ? count_ge(lo) : valid;
     if (want > 0 && kept <= 256) {
       __shared__ float s_sc2[256];
       __shared__ int s_ix2[256];
@@ -1144,9 +1157,10 @@ match_finalize_kernel(const FinalizeParams p) {
       __syncthreads();
     }
   }
-  // exact re-score of the best kRescore survivors
+  // exact re-score of the best R survivors (R = p.rescore <= kRescore; slots beyond R stay empty)
+  const int R = p.rescore;
   for (int c = warp; c < kRescore; c += 4) {
-    const int gi = s_ix[c];
+    const int gi = c < R ? s_ix[c] : -1;
     double sc = 0.0;
     if (gi >= 0) sc = warp_dot512_f64(p.gallery + static_cast<size_t>(gi) * 512, s_probe, lane);
     if (lane == 0) {
@@ -1187,7 +1201,7 @@ match_finalize_kernel(const FinalizeParams p) {
     int flag = 0;
     if (kk > 0) {
       float bound = s_excl;
-      if (Cp > kRescore && s_ix[kRescore] >= 0) bound = fmaxf(bound, s_sc[kRescore]);
+      if (Cp > R && s_ix[R] >= 0) bound = fmaxf(bound, s_sc[R]);
       if (bound > -INFINITY) {
         float pn = 0.f;
         for (int i = 0; i < 512; ++i) pn += s_probe[i] * s_probe[i];

@@ -6,18 +6,22 @@
 // image rows; per row, thread x packs pixel x's 27 inputs (+5 zeros) into a 64-byte K-major row of a
 // 128B-swizzled shared-memory tile, one elected thread issues two 128x64x16 tcgen05.mma, and the same
 // threads run the epilogue (TMEM -> +bias -> PReLU -> bf16 -> swizzled smem tile -> one TMA store of
-// the whole 112-pixel x 64-channel row, 14 KB contiguous in NHWC).  Several small CTAs per SM overlap gather, MMA and
-// store by occupancy.  Measured (profiles/r02_summary.md): the kernel is bound by instruction issue / latency of the
-// per-row chain, not by HBM (2.4 TB/s with one thread per pixel); round 2 therefore splits every pixel between TWO
-// threads (256 per CTA: K halves in the gather, channel halves in the epilogue).  A two-rows-per-MMA-step variant
-// (block-diagonal weights, N = 128) was tried first and was slower (175 vs 155 us: more registers, 3 CTAs per SM).
+// the whole 112-pixel x 64-channel row, 14 KB contiguous in NHWC).  The kernel is HBM-write bound
+// (128 B out per 6 B in); several small CTAs per SM overlap gather, MMA and store by occupancy.
+//
+// Round 2 tried two restructurings, both bit-identical and neither faster under ncu (profiles/r02_summary.md), which
+// is what a kernel bound by the WRITE stream (not by its instruction chain) looks like: (1) two image rows per MMA step
+// (block-diagonal [128][64] weights, N = 128, 3 CTAs per SM): 175 us against 155 us; (2) two threads per pixel (256
+// threads, K halves in the gather, channel halves in the epilogue): 153 us on a box where every other kernel ran 8 %
+// faster than in round 1.  The kernel writes 411 MB per batch of 256 at 2.65 TB/s; a plain device memset on the same
+// part is the yardstick for a write-only stream (tools/hbm_rw_peaks.py), not the read+write copy figure.
 #pragma once
 #include "ptx.cuh"
 
 namespace frb {
 
 constexpr int kStemRows = 8;          // image rows per CTA
-constexpr int kStemThreads = 256;      // two threads per pixel of a row
+constexpr int kStemThreads = 128;
 constexpr int kStemInStride = 352;    // bf16 elements per staged input row: 8 lead (5 unused + 1 zero pixel) + 336 + 8
 constexpr int kStemSmemBytes = 16384 /*A*/ + 8192 /*B*/ + 16384 /*out*/ + (kStemRows + 2) * kStemInStride * 2 + 512 + 64 + 1024;
 
@@ -90,38 +94,23 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
   uint32_t phase = 0;
 
   for (int ry = 0; ry < kStemRows; ++ry) {
-    // ---- gather: pixel x = tid & 127, K half = tid >> 7 (k 0..15 | 16..31); K index (r*3+s)*3+c = 9 contiguous staged
-    // values per filter row r, so half 0 takes row 0 and seven values of row 1, half 1 the rest and the five zeros
-    {
-      const int px = tid & 127, kh = tid >> 7;
-      if (px < W) {
-        unsigned short e[16];
-        const unsigned short* r0 = reinterpret_cast<const unsigned short*>(sIn + (ry + 0) * kStemInStride + 5 + 3 * px);
-        const unsigned short* r1 = reinterpret_cast<const unsigned short*>(sIn + (ry + 1) * kStemInStride + 5 + 3 * px);
-        const unsigned short* r2 = reinterpret_cast<const unsigned short*>(sIn + (ry + 2) * kStemInStride + 5 + 3 * px);
-        if (kh == 0) {
+    // ---- gather: pixel x = tid, K index (r*3+s)*3+c = 9 contiguous staged values per filter row r
+    if (tid < W) {
+      uint32_t pk[16];
+      unsigned short e[32];
 #pragma unroll
-          for (int q = 0; q < 9; ++q) e[q] = r0[q];
+      for (int r = 0; r < 3; ++r) {
+        const unsigned short* src = reinterpret_cast<const unsigned short*>(sIn + (ry + r) * kStemInStride + 5 + 3 * tid);
 #pragma unroll
-          for (int q = 0; q < 7; ++q) e[9 + q] = r1[q];
-        } else {
-          e[0] = r1[7];
-          e[1] = r1[8];
-#pragma unroll
-          for (int q = 0; q < 9; ++q) e[2 + q] = r2[q];
-#pragma unroll
-          for (int q = 11; q < 16; ++q) e[q] = 0;
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint4 v;
-          v.x = static_cast<uint32_t>(e[8 * c]) | (static_cast<uint32_t>(e[8 * c + 1]) << 16);
-          v.y = static_cast<uint32_t>(e[8 * c + 2]) | (static_cast<uint32_t>(e[8 * c + 3]) << 16);
-          v.z = static_cast<uint32_t>(e[8 * c + 4]) | (static_cast<uint32_t>(e[8 * c + 5]) << 16);
-          v.w = static_cast<uint32_t>(e[8 * c + 6]) | (static_cast<uint32_t>(e[8 * c + 7]) << 16);
-          *reinterpret_cast<uint4*>(sA + px * 128 + (((kh * 2 + c) ^ (px & 7)) << 4)) = v;
-        }
+        for (int q = 0; q < 9; ++q) e[r * 9 + q] = src[q];
       }
+#pragma unroll
+      for (int q = 27; q < 32; ++q) e[q] = 0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) pk[q] = static_cast<uint32_t>(e[2 * q]) | (static_cast<uint32_t>(e[2 * q + 1]) << 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(sA + tid * 128 + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
     }
     if (tid == 0) tma_store_wait_read<0>();  // the previous row's store has finished reading sOut
     fence_proxy_async();
@@ -136,13 +125,13 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (its pixels), columns 32 (w >> 2) .. +31 (its channel half)
-    {
-      const int px = (warp & 3) * 32 + (tid & 31), c = warp >> 2;
+    // ---- epilogue: thread = pixel (TMEM lane), 64 channels in two 32-column loads
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
       uint32_t r[32];
-      tmem_ld_32x32(tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + c * 32, r);
+      tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, r);
       tmem_ld_wait();
-      if (px < W) {
+      if (tid < W) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float v[8];
@@ -156,7 +145,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
           o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
           o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
           const int chunk = c * 4 + j;
-          *reinterpret_cast<uint4*>(sOut + px * 128 + ((chunk ^ (px & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(sOut + tid * 128 + ((chunk ^ (tid & 7)) << 4)) = o;
         }
       }
     }

@@ -230,6 +230,10 @@ int frb_debug_conv(frb_ctx* ctx, const frb_layer_desc* layer, int B, const void*
 int frb_debug_im2col(frb_ctx* ctx, const void* d_in, int B, int H, int W, int C, int ksize, int stride, int pad,
                      int m0, int c0, int tap_r, int tap_s, void* d_out_16k, void* stream);
 
+/* probe: read-only (mode 0) / write-only (mode 1) HBM stream over d_buf; h_ms = average pass duration.  The yardstick for
+ * kernels that only read (match filter) or only write (stem); MEASURED_PEAKS.json holds the read+write copy figure. */
+int frb_debug_stream_bw(frb_ctx* ctx, void* d_buf, size_t bytes, int mode, int iters, float* h_ms);
+
 /* probe: tcgen05.mma over a 128B-swizzled A operand starting j0 rows into a TMA-written slab
  * (mode 1 sets the descriptor's base_offset field).  D[128][64] = slab[j0:j0+128] * B^T */
 int frb_debug_shift_mma(frb_ctx* ctx, const void* d_slab_256x64, const void* d_B_64x64, int j0, int mode,
