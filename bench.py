@@ -347,8 +347,20 @@ def run_ours(args):
     # ---- BASELINE configs[2]: 4096 probes x N gallery, top-5.  One GPU: the whole gallery; N GPUs: sharded by identity,
     # probes split across the ranks, exchange + merge inside the timed region (dist.ShardedGallery).
     P3 = 4096
+    # probes per SURVEY 8d: enrolled rows + N(0, sigma) noise (a true top-1 with a margin), every 7th a pure-random impostor
     g3 = torch.Generator(device=dev).manual_seed(77)          # same seed on every rank: the same probe set everywhere
-    probes3 = torch.randn((P3, 512), generator=g3, device=dev)
+    rows3 = torch.randint(0, N, (P3,), generator=g3, device=dev)
+    probes3 = G[rows3] + 0.03 * torch.randn((P3, 512), generator=g3, device=dev) if world > 1 else None
+    if probes3 is None:       # one GPU: the fp32 generator copy of the gallery is gone, regenerate the chosen rows' blocks
+        probes3 = torch.empty((P3, 512), dtype=torch.float32, device=dev)
+        gg = torch.Generator(device=dev).manual_seed(1234)
+        for s0 in range(0, N, 1 << 18):
+            blk = torch.randn((min(1 << 18, N - s0), 512), generator=gg, device=dev)
+            blk = blk / blk.norm(dim=1, keepdim=True)
+            sel = (rows3 >= s0) & (rows3 < s0 + blk.shape[0])
+            probes3[sel] = blk[rows3[sel] - s0]
+        probes3 += 0.03 * torch.randn((P3, 512), generator=g3, device=dev)
+    probes3[::7] = torch.randn((probes3[::7].shape[0], 512), generator=g3, device=dev)
     sc3 = torch.empty((P3, topk), dtype=torch.float32, device=dev)
     ix3 = torch.empty((P3, topk), dtype=torch.int64, device=dev)
     ac3 = torch.empty((P3,), dtype=torch.uint8, device=dev)

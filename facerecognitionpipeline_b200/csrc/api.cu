@@ -575,7 +575,7 @@ int setup_slab(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, c
   const int need = (128 + 2 * (W + 2) + 2) * 128;
   sp->slab_bytes = std::max((need + 1023) / 1024 * 1024, (sp->box_bytes + 1023) / 1024 * 1024);
   const int b_bytes = (L.cout / 2) * 128;
-  const int misc = 1024 + 10 * L.cout * 4 + 1024;
+  const int misc = 1024 + 10 * L.cout * 4 + 9 * kBiasPad * 4 + 1024;
   const int total = 227 * 1024;
   // A unit (one 64-channel chunk of a tile's slab) is only 36 MMAs (0.6-2.4 us): several must be in flight
   // to hide the ~2 us load latency.  Weights stay resident when three units still fit beside them.

@@ -49,7 +49,7 @@ conv_slab_multi_sm100_kernel(const SlabLayer* __restrict__ layers, int num_layer
   uint64_t* tmem_empty_bar = tmem_full_bar + 4;           // [4] leader only, 16 arrivals
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 4);
   float* s_bias = reinterpret_cast<float*>(tail + 1024);      // [9][BLOCK_N]
-  float* s_prelu = s_bias + 9 * BLOCK_N;
+  float* s_prelu = s_bias + 9 * (BLOCK_N + kBiasPad);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -253,7 +253,7 @@ conv_slab_multi_sm100_kernel(const SlabLayer* __restrict__ layers, int num_layer
       rot = (rot + total_pairs) % pair_step;
       // this layer's epilogue constants (all eight warps are done with the previous layer's)
       if (l > 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = epi_tid; i < p.bias_cases * BLOCK_N; i += 256) s_bias[i] = p.bias[i];
+      for (int i = epi_tid; i < p.bias_cases * BLOCK_N; i += 256) s_bias[(i / BLOCK_N) * (BLOCK_N + kBiasPad) + (i % BLOCK_N)] = p.bias[i];
       if (p.prelu != nullptr)
         for (int i = epi_tid; i < BLOCK_N; i += 256) s_prelu[i] = p.prelu[i];
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -274,7 +274,7 @@ conv_slab_multi_sm100_kernel(const SlabLayer* __restrict__ layers, int num_layer
             bias_case = rc * 3 + cc;
           }
         }
-        const float* bias_row = s_bias + bias_case * BLOCK_N;
+        const float* bias_row = s_bias + bias_case * (BLOCK_N + kBiasPad);
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;

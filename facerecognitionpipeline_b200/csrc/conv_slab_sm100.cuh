@@ -103,7 +103,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   uint64_t* tmem_empty_bar = tmem_full_bar + 4;           // [4] leader only, 16 arrivals
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 4);
   float* s_bias = reinterpret_cast<float*>(tail + 1024);      // [9][BLOCK_N]
-  float* s_prelu = s_bias + 9 * BLOCK_N;
+  float* s_prelu = s_bias + 9 * (BLOCK_N + kBiasPad);
 
   // shuffle-broadcast makes the warp index provably warp-uniform for ptxas (uniform branches / registers)
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -141,7 +141,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     tmem2_alloc(tmem_ptr_smem, kAcc * BLOCK_N);
     tmem2_relinquish();
   }
-  for (int i = threadIdx.x; i < p.bias_cases * BLOCK_N; i += kGemm2Threads) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.bias_cases * BLOCK_N; i += kGemm2Threads) s_bias[(i / BLOCK_N) * (BLOCK_N + kBiasPad) + (i % BLOCK_N)] = p.bias[i];
   if (p.prelu != nullptr)
     for (int i = threadIdx.x; i < BLOCK_N; i += kGemm2Threads) s_prelu[i] = p.prelu[i];
   tc_fence_before();
@@ -364,7 +364,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           bias_case = rc * 3 + cc;
         }
       }
-      const float* bias_row = s_bias + bias_case * BLOCK_N;
+      const float* bias_row = s_bias + bias_case * (BLOCK_N + kBiasPad);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 64 && pair == first_pair) SLAB_TRACE(8);

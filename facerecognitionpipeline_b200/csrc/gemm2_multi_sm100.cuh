@@ -44,7 +44,7 @@ gemm2_multi_sm100_kernel(const Gemm2Layer* __restrict__ layers, int num_layers, 
   uint64_t* tmem_empty_bar = tmem_full_bar + S::kAccStages;  // leader only: 8 epilogue warps arrive
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + S::kAccStages);
   float* s_bias = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + 512);  // [cases][BLOCK_N]
-  float* s_prelu = s_bias + 9 * BLOCK_N;                                               // [BLOCK_N]
+  float* s_prelu = s_bias + 9 * (BLOCK_N + kBiasPad);                                               // [BLOCK_N]
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -251,7 +251,7 @@ gemm2_multi_sm100_kernel(const Gemm2Layer* __restrict__ layers, int num_layers, 
       // this layer's epilogue constants (the previous layer's readers are past the barrier at its end)
       if (p.progress != nullptr && l > 0) asm volatile("bar.sync 1, 256;" ::: "memory");  // flow mode has no end-of-layer barrier
       if (p.N == BLOCK_N) {
-        for (int i = epi_tid; i < p.bias_cases * BLOCK_N; i += 256) s_bias[i] = p.bias[i];
+        for (int i = epi_tid; i < p.bias_cases * BLOCK_N; i += 256) s_bias[(i / BLOCK_N) * (BLOCK_N + kBiasPad) + (i % BLOCK_N)] = p.bias[i];
         if (p.prelu != nullptr)
           for (int i = epi_tid; i < BLOCK_N; i += 256) s_prelu[i] = p.prelu[i];
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -283,12 +283,12 @@ gemm2_multi_sm100_kernel(const Gemm2Layer* __restrict__ layers, int num_layers, 
         if (p.N != BLOCK_N) {  // several N tiles (Cout = 512): refresh the constants of this tile
           asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
           for (int i = epi_tid; i < p.bias_cases * BLOCK_N; i += 256)
-            s_bias[i] = p.bias[(i / BLOCK_N) * p.N + n0 + (i % BLOCK_N)];
+            s_bias[(i / BLOCK_N) * (BLOCK_N + kBiasPad) + (i % BLOCK_N)] = p.bias[(i / BLOCK_N) * p.N + n0 + (i % BLOCK_N)];
           if (p.prelu != nullptr)
             for (int i = epi_tid; i < BLOCK_N; i += 256) s_prelu[i] = p.prelu[n0 + i];
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        const float* bias_row = s_bias + bias_case * BLOCK_N;
+        const float* bias_row = s_bias + bias_case * (BLOCK_N + kBiasPad);
 
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();

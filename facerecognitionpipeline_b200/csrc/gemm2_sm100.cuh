@@ -174,6 +174,11 @@ __device__ __forceinline__ bool tile_item(int it, int unit, int units, int total
 }
 
 constexpr int kGemm2Threads = 320;  // producer warp + MMA warp + 8 epilogue warps
+// The per-pixel bias table (9 border cases x Cout) is read with 16-byte loads by lanes that sit on different cases
+// (a warp's 32 pixels span image rows and borders).  With a row pitch of Cout floats all cases fall on the same
+// banks: ncu counted 3.4 extra wavefronts per load in the persistent run (34 M bank conflicts, the most sampled
+// instruction of its epilogue).  Four floats of padding per row put neighbouring cases on neighbouring bank groups.
+constexpr int kBiasPad = 4;
 
 template <int BLOCK_N>
 struct Gemm2Smem {
@@ -183,7 +188,7 @@ struct Gemm2Smem {
   static constexpr int kStages = (BLOCK_N == 256) ? 6 : (BLOCK_N == 128 ? 8 : 9);
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kEpiBytes = 10 * BLOCK_N * 4;  // bias table [<=9][BLOCK_N] + PReLU [BLOCK_N], fp32
+  static constexpr int kEpiBytes = 10 * BLOCK_N * 4 + 9 * kBiasPad * 4;  // bias table [<=9][BLOCK_N + pad] + PReLU [BLOCK_N], fp32
   static constexpr int kTotal = kStages * kStageBytes + 512 + kEpiBytes + 1024;
 };
 
@@ -207,7 +212,7 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tmem_empty_bar = tmem_full_bar + S::kAccStages;  // leader only: 8 epilogue warps arrive
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + S::kAccStages);
   float* s_bias = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + 512);  // [cases][BLOCK_N]
-  float* s_prelu = s_bias + 9 * BLOCK_N;                                               // [BLOCK_N]
+  float* s_prelu = s_bias + 9 * (BLOCK_N + kBiasPad);                                               // [BLOCK_N]
 
   // shuffle-broadcast makes the warp index provably warp-uniform for ptxas (uniform branches / registers)
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -250,7 +255,7 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // Per-layer epilogue constants live in shared memory (they were a ~400-cycle global-load stall per
   // 32-column chunk).  With one N tile they are loaded once; Cout = 512 reloads per tile below.
   if (p.N == BLOCK_N) {
-    for (int i = threadIdx.x; i < p.bias_cases * BLOCK_N; i += kGemm2Threads) s_bias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < p.bias_cases * BLOCK_N; i += kGemm2Threads) s_bias[(i / BLOCK_N) * (BLOCK_N + kBiasPad) + (i % BLOCK_N)] = p.bias[i];
     if (p.prelu != nullptr)
       for (int i = threadIdx.x; i < BLOCK_N; i += kGemm2Threads) s_prelu[i] = p.prelu[i];
   }
@@ -417,12 +422,12 @@ gemm2_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (p.N != BLOCK_N) {  // several N tiles (Cout = 512): refresh the constants of this tile
         asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
         for (int i = epi_tid; i < p.bias_cases * BLOCK_N; i += 256)
-          s_bias[i] = p.bias[(i / BLOCK_N) * p.N + n0 + (i % BLOCK_N)];
+          s_bias[(i / BLOCK_N) * (BLOCK_N + kBiasPad) + (i % BLOCK_N)] = p.bias[(i / BLOCK_N) * p.N + n0 + (i % BLOCK_N)];
         if (p.prelu != nullptr)
           for (int i = epi_tid; i < BLOCK_N; i += 256) s_prelu[i] = p.prelu[n0 + i];
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      const float* bias_row = s_bias + bias_case * BLOCK_N;
+      const float* bias_row = s_bias + bias_case * (BLOCK_N + kBiasPad);
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();

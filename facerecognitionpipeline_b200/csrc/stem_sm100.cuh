@@ -94,23 +94,41 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
   uint32_t phase = 0;
 
   for (int ry = 0; ry < kStemRows; ++ry) {
-    // ---- gather: pixel x = tid, K index (r*3+s)*3+c = 9 contiguous staged values per filter row r
+    // ---- gather: pixel x = tid, K index (r*3+s)*3+c = 9 contiguous staged values (18 bytes) per filter row r.
+    // ncu (profiles/r02_summary.md): this kernel is bound by the shared-memory data pipe (75 % of its wavefront peak),
+    // most of it the 27 two-byte GENERIC loads per pixel this gather used to issue (7.5 wavefronts each).  Now: five
+    // aligned ld.shared.u32 per filter row and funnel shifts - pixel x starts at byte 10 + 6x of the staged row, i.e. on
+    // a word boundary for odd x and one halfword past it for even x.
     if (tid < W) {
-      uint32_t pk[16];
-      unsigned short e[32];
+      const uint32_t hp = (tid & 1) ? 0u : 16u;                         // halfword phase of this pixel inside its first word
+      const uint32_t row0 = smem_u32(sIn) + static_cast<uint32_t>(ry) * (kStemInStride * 2) + ((10u + 6u * tid) & ~3u);
+      uint32_t w[3][6];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        const unsigned short* src = reinterpret_cast<const unsigned short*>(sIn + (ry + r) * kStemInStride + 5 + 3 * tid);
 #pragma unroll
-        for (int q = 0; q < 9; ++q) e[r * 9 + q] = src[q];
+        for (int j = 0; j < 5; ++j)
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[r][j]) : "r"(row0 + r * (kStemInStride * 2) + 4 * j));
+        w[r][5] = 0u;
       }
+      // S(r, j) = values (2j, 2j+1) of filter row r; T(j) = values (2j+1, 2j+2) of filter row 1 (it starts at odd k = 9)
+      uint32_t pk[16];
 #pragma unroll
-      for (int q = 27; q < 32; ++q) e[q] = 0;
+      for (int j = 0; j < 4; ++j) pk[j] = __funnelshift_r(w[0][j], w[0][j + 1], hp);                  // k 0..7
+      const uint32_t e08 = __funnelshift_r(w[0][4], 0u, hp) & 0xffffu;                                 // k 8
+      const uint32_t e10 = __funnelshift_r(w[1][0], 0u, hp) & 0xffffu;                                 // k 9
+      pk[4] = e08 | (e10 << 16);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) pk[q] = static_cast<uint32_t>(e[2 * q]) | (static_cast<uint32_t>(e[2 * q + 1]) << 16);
+      for (int j = 0; j < 4; ++j) pk[5 + j] = __funnelshift_rc(w[1][j], w[1][j + 1], 16u + hp);       // k 10..17
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[9 + j] = __funnelshift_r(w[2][j], w[2][j + 1], hp);              // k 18..25
+      pk[13] = __funnelshift_r(w[2][4], 0u, hp) & 0xffffu;                                            // k 26, 27 = 0
+      pk[14] = 0u;
+      pk[15] = 0u;
+      const uint32_t a_row = smem_u32(sA) + tid * 128;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(sA + tid * 128 + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_row + ((c ^ (tid & 7)) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                     "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
     }
     if (tid == 0) tma_store_wait_read<0>();  // the previous row's store has finished reading sOut
     fence_proxy_async();
@@ -134,18 +152,25 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
       if (tid < W) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float v[8];
+          float v[8], bz[8], pz[8];
+          // explicit ld.shared.v4 (a broadcast: one wavefront each); the generic loads the compiler emitted for
+          // s_bias[ch] / s_prelu[ch] were the other half of this kernel's shared-memory wavefronts
+          const uint32_t bo = smem_u32(s_bias) + (c * 32 + j * 8) * 4, po = smem_u32(s_prelu) + (c * 32 + j * 8) * 4;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bz[0]), "=f"(bz[1]), "=f"(bz[2]), "=f"(bz[3]) : "r"(bo));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bz[4]), "=f"(bz[5]), "=f"(bz[6]), "=f"(bz[7]) : "r"(bo + 16));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pz[0]), "=f"(pz[1]), "=f"(pz[2]), "=f"(pz[3]) : "r"(po));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pz[4]), "=f"(pz[5]), "=f"(pz[6]), "=f"(pz[7]) : "r"(po + 16));
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            const int ch = c * 32 + j * 8 + t;
-            const float a = __uint_as_float(r[j * 8 + t]) + s_bias[ch];
-            v[t] = a > 0.f ? a : a * s_prelu[ch];
+            const float a = __uint_as_float(r[j * 8 + t]) + bz[t];
+            v[t] = a > 0.f ? a : a * pz[t];
           }
           uint4 o;
           o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
           o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
           const int chunk = c * 4 + j;
-          *reinterpret_cast<uint4*>(sOut + tid * 128 + ((chunk ^ (tid & 7)) << 4)) = o;
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(sOut) + tid * 128 + ((chunk ^ (tid & 7)) << 4)), "r"(o.x),
+                       "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
         }
       }
     }

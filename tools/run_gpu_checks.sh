@@ -1,14 +1,16 @@
 #!/bin/bash
 # One GPU-box pass: the -m gpu suite, the default bench line, schedule A/B runs (bit-identity + timing).
-#   gpurun --timeout 1700 -- 'bash tools/run_gpu_checks.sh <tag> [ab]'
+#   gpurun --timeout 1700 -- 'bash tools/run_gpu_checks.sh <tag> [all|ab|abonly|summary]'   (summary: only digest gpurun_out/<tag>_bench*.log)
 # Writes gpurun_out/<tag>_*.log; prints a short summary.
 tag=${1:-run}; mode=${2:-all}
 mkdir -p gpurun_out
-if [ "$mode" != "abonly" ]; then
+if [ "$mode" != "abonly" ] && [ "$mode" != "summary" ]; then
   (timeout 1300 python -m pytest tests -m gpu -x -q 2>&1 | tail -40) > gpurun_out/${tag}_pytest.log 2>&1
   tail -4 gpurun_out/${tag}_pytest.log
 fi
+if [ "$mode" != "summary" ]; then
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench.log 2>&1
+fi
 if [ "$mode" = "ab" ] || [ "$mode" = "abonly" ]; then
   for m in 0 1; do for b in 8 256; do
     FRB_SLAB_MULTI=$m timeout 300 python tools/diag_multi.py ${tag}_sm${m}_$b ir_101 $b 2>&1 | tail -1
