@@ -38,7 +38,10 @@ struct SlabParams {
   int* progress;         // inter-layer dataflow counters (ptx.cuh); nullptr = whole-grid dependency
   int wait_target;
   int sig_fence;         // experiments only: 0 drops the release fence (UNSAFE)
+  int stage_out;         // 1: the epilogue stages a tile's output in shared memory and ONE TMA store writes it (tmOut)
 };
+
+constexpr int kSlabStageBytes = 2 * 16384;   // two staging buffers of 112 pixels x 64 channels (swizzled 128-byte rows)
 
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
                                              int c2, int c3) {
@@ -85,7 +88,7 @@ constexpr int kSlabMaxBuf = 6;
 template <int BLOCK_N, int CHUNKS>
 __global__ void __launch_bounds__(kGemm2Threads, 1)
 conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
-                       const SlabParams p) {
+                       const __grid_constant__ CUtensorMap tmOut, const SlabParams p) {
   constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;
   constexpr int kAcc = (512 / BLOCK_N) < 4 ? (512 / BLOCK_N) : 4;  // TMEM accumulator stages
   constexpr int kNumKb = 9 * CHUNKS;
@@ -93,7 +96,8 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_slab = smem;                                  // [nbuf][slab_bytes]
   uint8_t* smem_b = smem + p.nbuf * p.slab_bytes;             // [b_stages][kBBytes]
-  uint8_t* tail = smem_b + p.b_stages * kBBytes;
+  uint8_t* smem_stage = smem_b + p.b_stages * kBBytes;        // [2][16 KB] output staging (only with p.stage_out)
+  uint8_t* tail = smem_stage + (p.stage_out ? kSlabStageBytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* slab_full = bars;                             // [6]  leader only
   uint64_t* slab_empty = bars + kSlabMaxBuf;              // [6]  per CTA
@@ -123,6 +127,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmB);
+    if (p.stage_out) prefetch_tmap(&tmOut);
     for (int i = 0; i < kSlabMaxBuf; ++i) {
       mbar_init(&slab_full[i], 1);
       mbar_init(&slab_empty[i], 1);
@@ -343,10 +348,19 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
   } else {
     // ===================== epilogue warps 2..9 =====================
+    // Output path.  Direct: every thread stores its pixel's 64-byte pieces straight to global memory - a warp store
+    // then touches 32 different 128-byte lines, and ncu showed the LSU data pipe at 78 % of its wavefront peak in the
+    // 112x112 layer (tensor pipe 46 %, HBM 2.7 TB/s: profiles/r02_summary.md).  Staged (p.stage_out, the Cout = 64
+    // layers): the tile's 112 x 64-channel block goes to a swizzled shared-memory buffer (conflict-free 16-byte
+    // stores) and ONE TMA store per tile writes its 14 KB, contiguous in NHWC; two buffers, so the store of tile n
+    // drains while tile n + 1 is computed.  Same values, same rounding: no bit changes.
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
+    const bool staged = p.stage_out != 0;
+    const int epi_tid = threadIdx.x - 64;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int stage_buf = 0;
     for (int pair = first_pair; pair < total_pairs; pair += pair_step) {
       const int tile = pair * 2 + crank;
       const int i = quad * 32 + lane;           // accumulator row = padded position in the tile
@@ -414,21 +428,45 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
               }
             }
           }
-          uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.N + c * 32);
+          if (staged) {
+            const int t = ri * p.W + wi;                       // pixel of the tile, row of the staging buffer
+            const uint32_t row = smem_u32(smem_stage) + stage_buf * 16384 + t * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            dst[j] = o;
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t ox = pack_bf16x2(v[8 * j], v[8 * j + 1]), oy = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              const uint32_t oz = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), ow = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((c * 4 + j) ^ (t & 7)) << 4)), "r"(ox), "r"(oy),
+                           "r"(oz), "r"(ow) : "memory");
+            }
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.N + c * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              dst[j] = o;
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      if (staged) {
+        // the store of the PREVIOUS tile (other buffer) must have finished reading before the NEXT tile overwrites it:
+        // the issuing thread waits for it here, everybody learns through the barrier
+        if (epi_tid == 0) tma_store_wait_read<0>();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (epi_tid == 0 && tile < num_tiles) {
+          tma_store_2d(&tmOut, smem_stage + stage_buf * 16384, 0, tile * (p.R * p.W));
+          tma_store_commit();
+        }
+        stage_buf ^= 1;
+      }
       if (p.progress != nullptr) signal_rows(p.progress, valid, img, BLOCK_N / 64, p.sig_fence != 0);
       if (++acc == kAcc) {
         acc = 0;
@@ -438,6 +476,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   }
 
   if (threadIdx.x == 64) SLAB_TRACE(10);
+  if (p.stage_out && threadIdx.x == 64) tma_store_wait<0>();   // the staging buffers are read until the stores complete
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
