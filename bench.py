@@ -407,14 +407,40 @@ def run_ours(args):
             flag = torch.tensor([int(same)], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             ms = timed(lambda: sg.match(mine, k=topk, thr=thr, n_probes=P3), 20)
-            res[mode] = dict(ms=ms, ids_identical_to_unsharded=bool(flag.item()))
+            res[mode] = dict(ms=ms, ids_identical_to_unsharded=bool(flag.item()),
+                             rows_through_exact_fixup=int(ctx._lib.frb_match_last_flagged(ctx.handle)))
+        # where the time goes (NCCL exchange, same steps timed one by one with events; max over ranks each)
+        from facerecognitionpipeline_b200.dist import all_gather_balanced
+        parts = None
+        try:
+            rec = torch.empty((P3, topk, 2), dtype=torch.int64, device=dev)
+            every = torch.empty((world, P3, topk, 2), dtype=torch.int64, device=dev)
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(10)]
+            barrier()
+            for it in range(10):
+                evs[it][0].record(stream)
+                allp = all_gather_balanced(mine, P3)
+                evs[it][1].record(stream)
+                ctx.frb_match_packed(allp.data_ptr(), P3, topk, thr, 1, rec.data_ptr(), st)
+                evs[it][2].record(stream)
+                dist.all_gather_into_tensor(every.view(-1), rec.view(-1))
+                ctx.frb_topk_merge_packed(every.data_ptr(), world, P3, topk, thr, sc3.data_ptr(), ix3.data_ptr(), ac3.data_ptr(), st)
+                evs[it][3].record(stream)
+            torch.cuda.synchronize(dev)
+            barrier()
+            tt = [float(np.mean([evs[it][j].elapsed_time(evs[it][j + 1]) for it in range(2, 10)])) for j in range(3)]
+            parts = dict(probe_all_gather=max_over_ranks(tt[0]), local_match=max_over_ranks(tt[1]),
+                         record_all_gather_and_merge=max_over_ranks(tt[2]),
+                         note="event-separated steps of the NCCL exchange; a collective's time includes waiting for the slowest rank")
+        except Exception as ex:
+            parts = dict(error=str(ex)[:200])
         best = min((m for m in res if "ms" in res[m]), key=lambda m: res[m]["ms"])
         sharded = dict(workload=f"{P3} probes x {N} x 512 gallery, top-{topk}, gallery sharded by identity over {world} GPUs, "
                                 f"probes split over the ranks; probe exchange + per-shard match + top-k exchange + merge timed",
                        exchange=best, sharded_match_ms=res[best]["ms"], sharded_probes_per_s=P3 / (res[best]["ms"] / 1e3),
                        one_gpu_match_ms=c3_1gpu_ms, sharded_vs_1gpu=c3_1gpu_ms / res[best]["ms"],
                        strong_scaling_efficiency=c3_1gpu_ms / res[best]["ms"] / world,
-                       tflops=P3 * 1024.0 * N / (res[best]["ms"] / 1e3) / 1e12, by_exchange=res)
+                       tflops=P3 * 1024.0 * N / (res[best]["ms"] / 1e3) / 1e12, by_exchange=res, nccl_parts_ms=parts)
         del G
         # back to the replicated gallery is not needed: everything below works on the embed path only
 

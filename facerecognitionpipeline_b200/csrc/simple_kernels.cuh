@@ -1322,6 +1322,13 @@ struct ExactFixParams {
   PeerPush push;
 };
 
+// Few listed rows (count <= gridDim.y, the usual case: zero or one): every row gets gridDim.y / count TIMES as many
+// gallery partitions, so a single flagged row is scanned by the whole grid (1184 blocks) instead of by 74 blocks -
+// one flagged row used to add ~0.3 ms to a sharded match of 4096 probes (profiles/r02_summary.md).
+__device__ __forceinline__ int exact_parts(int count, int blocks_x, int rows_y) {
+  return (count > 0 && count <= rows_y) ? blocks_x * (rows_y / count) : blocks_x;
+}
+
 __global__ void __launch_bounds__(256)
 match_exact_part_kernel(const ExactFixParams p) {
   __shared__ float s_probe[512];
@@ -1330,8 +1337,23 @@ match_exact_part_kernel(const ExactFixParams p) {
   pdl_launch_dependents();
   pdl_wait();
   const int count = *p.count;
+  if (count == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, k = p.k;
-  for (int f = blockIdx.y; f < count; f += gridDim.y) {
+  const int rows_y = static_cast<int>(gridDim.y), blocks_x = static_cast<int>(gridDim.x);
+  const int parts = exact_parts(count, blocks_x, rows_y);
+  int f_first, f_step, part;
+  if (count <= rows_y) {            // few rows: blockIdx.y = sub-partition * count + row
+    const int sub = blockIdx.y / count;
+    if (sub >= rows_y / count) return;
+    f_first = blockIdx.y % count;
+    f_step = count;                 // exactly one row per block
+    part = blockIdx.x * (rows_y / count) + sub;
+  } else {                          // many rows: they are strided over blockIdx.y, 74 partitions each
+    f_first = blockIdx.y;
+    f_step = rows_y;
+    part = blockIdx.x;
+  }
+  for (int f = f_first; f < count; f += f_step) {
     const int prow = p.rows[f];
     __syncthreads();   // the previous row's merge has read the lists
     for (int i = threadIdx.x; i < 512; i += 256) s_probe[i] = p.probes[static_cast<size_t>(prow) * 512 + i];
@@ -1340,7 +1362,7 @@ match_exact_part_kernel(const ExactFixParams p) {
       (&w_ix[0][0])[i] = -1;
     }
     __syncthreads();
-    for (long long g = static_cast<long long>(blockIdx.x) * 8 + warp; g < p.N; g += static_cast<long long>(gridDim.x) * 8) {
+    for (long long g = static_cast<long long>(part) * 8 + warp; g < p.N; g += static_cast<long long>(parts) * 8) {
       const double s = warp_dot512_f64(p.gallery + g * 512, s_probe, lane);
       if (lane == 0 && cand_before(s, g, w_sc[warp][k - 1], w_ix[warp][k - 1])) {
         int j = k - 1;   // sorted insertion (canonical order); rare once the list has settled
@@ -1356,7 +1378,7 @@ match_exact_part_kernel(const ExactFixParams p) {
     __syncthreads();
     if (threadIdx.x == 0) {   // 8-way merge of the sorted warp lists -> this block's best k
       int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      TopkRec* dst = p.part + (static_cast<size_t>(f) * gridDim.x + blockIdx.x) * k;
+      TopkRec* dst = p.part + (static_cast<size_t>(f) * parts + part) * k;
       for (int r = 0; r < k; ++r) {
         int bw = -1;
         for (int w = 0; w < 8; ++w)
@@ -1370,13 +1392,14 @@ match_exact_part_kernel(const ExactFixParams p) {
         dst[r] = rec;
       }
     }
+    if (count <= rows_y) break;
   }
 }
 
 // merge of a listed row's kExactBlocks partial lists: k rounds of block arg-max in canonical order (as
 // match_exact_topk_kernel), outputs for the probe row, and - sharded - the row goes to the peers
 __global__ void __launch_bounds__(128)
-match_exact_fix_kernel(const ExactFixParams p, int parts) {
+match_exact_fix_kernel(const ExactFixParams p, int blocks_x, int rows_y) {
   __shared__ double s_best[128];
   __shared__ long long s_besti[128];
   __shared__ double s_out[kExactMaxK];
@@ -1385,6 +1408,7 @@ match_exact_fix_kernel(const ExactFixParams p, int parts) {
   pdl_wait();
   const int count = *p.count;
   const int t = threadIdx.x, k = p.k;
+  const int parts = exact_parts(count, blocks_x, rows_y);   // as match_exact_part_kernel laid the lists out
   for (int f = blockIdx.x; f < count; f += gridDim.x) {
     const int prow = p.rows[f];
     const TopkRec* cand = p.part + static_cast<size_t>(f) * parts * k;

@@ -252,18 +252,20 @@ def test_config5_10m_identity_gallery_sharded_equals_unsharded(ctx):
     torch.cuda.empty_cache()
 
 
-def test_flagged_rows_are_fixed_on_the_device(ctx):
+@pytest.mark.parametrize("n_hit", [1, 5, 16, 17, 120])
+def test_flagged_rows_are_fixed_on_the_device(ctx, n_hit):
     """Rows whose filter proof fails are re-done by the exact fix-up kernels, which take the row list and its length
     from the device (no D2H + synchronise inside frb_match).  200 identical copies of one row defeat the proof (the
-    64 re-scored survivors tie with everything the filter kept below them); with 150 such probes the fix-up walks
-    its list in several strides (16 rows in flight in the partial kernel, 64 in the merge kernel)."""
+    re-scored survivors tie with everything the filter kept below them).  Up to 16 flagged rows are each scanned by a
+    multiple of the 74 gallery partitions (one flagged row: the whole grid); above that the fix-up walks its list in
+    strides (16 rows in flight in the partial kernel, 64 in the merge kernel)."""
     rng = np.random.default_rng(77)
     N, P, k = 30000, 150, 5
     G = _unit(rng.standard_normal((N, 512)))
     dup = np.sort(rng.choice(N, 200, replace=False))
     G[dup] = G[dup[0]]
     probes = _unit(rng.standard_normal((P, 512)))
-    hit = np.arange(0, P, 1)[::1][:120]
+    hit = np.sort(rng.choice(P, n_hit, replace=False))
     probes[hit] = _unit(G[dup[0]][None] + 0.02 * rng.standard_normal((len(hit), 512)))
     sc, ix, ac = _match(ctx, G, probes, k, thr=0.4)
     flagged = ctx._lib.frb_match_last_flagged(ctx.handle)
