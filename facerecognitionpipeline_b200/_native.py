@@ -136,7 +136,8 @@ def lib() -> C.CDLL:
             raise NativeError(
                 f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(or `make -C facerecognitionpipeline_b200/csrc`). There is no CPU fallback.")
-        l = C.CDLL(str(LIB_PATH))
+        # FRB_LIBRARY: load another build of the SAME library (A/B runs of compile-time variants); never a fallback
+        l = C.CDLL(os.environ.get("FRB_LIBRARY") or str(LIB_PATH))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype = res

@@ -1836,7 +1836,7 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
     CK(cudaMalloc(&ctx->d_cand_idx, n * 4));
     ctx->match_cap_slices = mp.slices;
   }
-  if (ensure(ctx, &ctx->d_exact_part, &ctx->exact_part_cap, static_cast<size_t>(std::max(P, kExactRowsY)) * kExactBlocks * k)) return 1;
+  if (ensure(ctx, &ctx->d_exact_part, &ctx->exact_part_cap, static_cast<size_t>(std::max(P, kExactRowsY * kExactRowsY)) * kExactBlocks * k)) return 1;
   mp.cand_score = ctx->d_cand_score;
   mp.cand_idx = ctx->d_cand_idx;
   mp.row_floor = ctx->d_row_floor;
@@ -1878,8 +1878,9 @@ int match_core(frb_ctx* ctx, const float* d_probe_f32, const __nv_bfloat16* d_pr
   xp.push = pp;
   CK(launch_pdl(match_exact_part_kernel, dim3(kExactBlocks, std::min(P, kExactRowsY)), dim3(256), 0, st, pdl, 1, xp));
   ctx->launches++;
-  CK(launch_pdl(match_exact_fix_kernel, dim3(std::min(P, 64)), dim3(128), 0, st, pdl, 1, xp, static_cast<int>(kExactBlocks),
-                std::min(P, kExactRowsY)));
+  if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_exact_fix_kernel), kExactFixSmemBytes)) return 1;
+  CK(launch_pdl(match_exact_fix_kernel, dim3(std::min(P, 64)), dim3(128), kExactFixSmemBytes, st, pdl, 1, xp,
+                static_cast<int>(kExactBlocks), std::min(P, kExactRowsY)));
   ctx->launches++;
   if (ctx->match_profiling) CK(cudaEventRecord(ctx->match_prof_ev[3], st));
   // frb_match_last_flagged: the count travels to pinned memory behind an event, read only when somebody asks
@@ -2196,7 +2197,7 @@ extern "C" int frb_xchg_create(frb_ctx* ctx, int world, int rank, int max_probes
   if (stage_match(ctx, max_probes, max_k)) return 1;
   double* s64 = nullptr;
   if (scores64_scratch(ctx, static_cast<size_t>(max_probes) * max_k, &s64)) return 1;
-  if (ensure(ctx, &ctx->d_exact_part, &ctx->exact_part_cap, static_cast<size_t>(std::max(max_probes, kExactRowsY)) * kExactBlocks * max_k)) return 1;
+  if (ensure(ctx, &ctx->d_exact_part, &ctx->exact_part_cap, static_cast<size_t>(std::max(max_probes, kExactRowsY * kExactRowsY)) * kExactBlocks * max_k)) return 1;
   if (ensure(ctx, &ctx->d_exact, &ctx->exact_elems, static_cast<size_t>(kExactChunk) * kExactOnlyBelow)) return 1;
   {
     const int slices = kMaxCandPad / kCand;   // the most the filter ever uses
@@ -2226,6 +2227,7 @@ extern "C" int frb_xchg_create(frb_ctx* ctx, int world, int rank, int max_probes
   // opt the kernels into their shared-memory sizes now as well
   if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_filter2_kernel), Match2Smem::kTotal)) return 1;
   if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_filter_kernel), MatchSmem::kTotal)) return 1;
+  if (set_smem_attr(ctx, reinterpret_cast<const void*>(match_exact_fix_kernel), kExactFixSmemBytes)) return 1;
   return 0;
 }
 

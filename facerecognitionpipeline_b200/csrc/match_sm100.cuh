@@ -20,7 +20,10 @@ namespace frb {
 constexpr int kMatchDim = 512;          // embedding size
 constexpr int kMatchKB = kMatchDim / 64;  // 8 K blocks
 constexpr int kMatchBN = 256;           // gallery rows per MMA tile
-constexpr int kCand = 8;                // candidates kept per (probe, slice)
+#ifndef FRB_KCAND
+#define FRB_KCAND 8
+#endif
+constexpr int kCand = FRB_KCAND;        // candidates kept per (probe, slice); a multiple of 4
 constexpr int kMatchBStages = 3;
 constexpr int kMatchThreads = 192;
 
@@ -320,10 +323,11 @@ match_filter_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_consta
         const size_t o = (static_cast<size_t>(row) * p.slices + gs) * kCand;
         float4* ds = reinterpret_cast<float4*>(p.cand_score + o);
         int4* di = reinterpret_cast<int4*>(p.cand_idx + o);
-        ds[0] = make_float4(ls[0], ls[1], ls[2], ls[3]);
-        ds[1] = make_float4(ls[4], ls[5], ls[6], ls[7]);
-        di[0] = make_int4(li[0], li[1], li[2], li[3]);
-        di[1] = make_int4(li[4], li[5], li[6], li[7]);
+#pragma unroll
+        for (int q = 0; q < kCand / 4; ++q) {
+          ds[q] = make_float4(ls[4 * q], ls[4 * q + 1], ls[4 * q + 2], ls[4 * q + 3]);
+          di[q] = make_int4(li[4 * q], li[4 * q + 1], li[4 * q + 2], li[4 * q + 3]);
+        }
       }
     }
   }
@@ -548,10 +552,11 @@ match_filter2_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
         const size_t o = (static_cast<size_t>(row) * p.slices + gs) * kCand;
         float4* ds = reinterpret_cast<float4*>(p.cand_score + o);
         int4* di = reinterpret_cast<int4*>(p.cand_idx + o);
-        ds[0] = make_float4(ls[0], ls[1], ls[2], ls[3]);
-        ds[1] = make_float4(ls[4], ls[5], ls[6], ls[7]);
-        di[0] = make_int4(li[0], li[1], li[2], li[3]);
-        di[1] = make_int4(li[4], li[5], li[6], li[7]);
+#pragma unroll
+        for (int q = 0; q < kCand / 4; ++q) {
+          ds[q] = make_float4(ls[4 * q], ls[4 * q + 1], ls[4 * q + 2], ls[4 * q + 3]);
+          di[q] = make_int4(li[4 * q], li[4 * q + 1], li[4 * q + 2], li[4 * q + 3]);
+        }
       }
     }
   }

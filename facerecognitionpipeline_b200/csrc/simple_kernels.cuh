@@ -936,6 +936,22 @@ __device__ __forceinline__ double warp_dot512_f64(const float* __restrict__ a, c
   return s;
 }
 
+// Same dot product with the probe's 16 values of this lane already converted to f64 (same order, same bits): the
+// float -> double conversions run on a slow pipe (ncu: they, not the loads or the DFMAs, bounded the exact kernels), and
+// a warp scores many gallery rows against the same probe.
+__device__ __forceinline__ void probe_lane_f64(const float* __restrict__ probe, int lane, double (&pd)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pd[j] = static_cast<double>(probe[lane + 32 * j]);
+}
+__device__ __forceinline__ double warp_dot512_f64_pre(const float* __restrict__ a, const double (&pd)[16], int lane) {
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s = fma(static_cast<double>(a[lane + 32 * j]), pd[j], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
 // canonical order: score descending, then index ascending; idx < 0 sorts last
 __device__ __forceinline__ bool cand_before(double sa, long long ia, double sb, long long ib) {
   if (ia < 0) return false;
@@ -1233,8 +1249,10 @@ match_exact_scores_kernel(const float* __restrict__ gallery, long long N, const 
   for (int i = threadIdx.x; i < 512; i += 256) s_probe[i] = probes[static_cast<size_t>(prow) * 512 + i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double pd[16];
+  probe_lane_f64(s_probe, lane, pd);
   for (long long g = static_cast<long long>(blockIdx.x) * 8 + warp; g < N; g += static_cast<long long>(gridDim.x) * 8) {
-    const double s = warp_dot512_f64(gallery + g * 512, s_probe, lane);
+    const double s = warp_dot512_f64_pre(gallery + g * 512, pd, lane);
     if (lane == 0) scores[static_cast<size_t>(f) * N + g] = s;
   }
 }
@@ -1322,48 +1340,107 @@ struct ExactFixParams {
   PeerPush push;
 };
 
-// Few listed rows (count <= gridDim.y, the usual case: zero or one): every row gets gridDim.y / count TIMES as many
-// gallery partitions, so a single flagged row is scanned by the whole grid (1184 blocks) instead of by 74 blocks -
-// one flagged row used to add ~0.3 ms to a sharded match of 4096 probes (profiles/r02_summary.md).
-__device__ __forceinline__ int exact_parts(int count, int blocks_x, int rows_y) {
-  return (count > 0 && count <= rows_y) ? blocks_x * (rows_y / count) : blocks_x;
+// Few listed rows (count <= gridDim.y, the usual case: zero to a handful) and k <= kExactFewK: ONE pass over the gallery
+// serves all of them - the whole grid (1184 blocks) partitions the gallery, a warp loads a gallery row into registers
+// once and scores it against every listed probe (all of them sit in shared memory).  A flagged row used to be scanned
+// by 74 blocks on its own: one flagged row added ~0.3 ms to a sharded match of 4096 probes, four rows 0.24 ms even with
+// the whole grid per row (profiles/r02_summary.md).  Larger k / more rows: one row at a time per block, rows strided
+// over blockIdx.y, 74 partitions each.
+constexpr int kExactFewK = 8;
+constexpr int kExactFewRows = 16;  // rows the one-pass path takes (= kExactRowsY)
+__device__ __forceinline__ int exact_parts(int count, int blocks_x, int rows_y, int k) {
+  return (count > 0 && count <= kExactFewRows && count <= rows_y && k <= kExactFewK) ? blocks_x * rows_y : blocks_x;
 }
 
 __global__ void __launch_bounds__(256)
 match_exact_part_kernel(const ExactFixParams p) {
-  __shared__ float s_probe[512];
-  __shared__ double w_sc[8][kExactMaxK];
-  __shared__ long long w_ix[8][kExactMaxK];
+  __shared__ float s_probe[kExactFewRows][512];                     // few-rows path: every listed probe; else row [0]
+  __shared__ double w_sc[8][kExactFewRows * kExactFewK];            // per warp: few-rows path [row][k]; else [kExactMaxK] (fits: 8*8 >= 32)
+  __shared__ int w_ix[8][kExactFewRows * kExactFewK];
+  static_assert(kExactFewRows * kExactFewK >= kExactMaxK, "list storage");
   pdl_launch_dependents();
   pdl_wait();
   const int count = *p.count;
   if (count == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, k = p.k;
   const int rows_y = static_cast<int>(gridDim.y), blocks_x = static_cast<int>(gridDim.x);
-  const int parts = exact_parts(count, blocks_x, rows_y);
-  int f_first, f_step, part;
-  if (count <= rows_y) {            // few rows: blockIdx.y = sub-partition * count + row
-    const int sub = blockIdx.y / count;
-    if (sub >= rows_y / count) return;
-    f_first = blockIdx.y % count;
-    f_step = count;                 // exactly one row per block
-    part = blockIdx.x * (rows_y / count) + sub;
-  } else {                          // many rows: they are strided over blockIdx.y, 74 partitions each
-    f_first = blockIdx.y;
-    f_step = rows_y;
-    part = blockIdx.x;
-  }
-  for (int f = f_first; f < count; f += f_step) {
-    const int prow = p.rows[f];
-    __syncthreads();   // the previous row's merge has read the lists
-    for (int i = threadIdx.x; i < 512; i += 256) s_probe[i] = p.probes[static_cast<size_t>(prow) * 512 + i];
-    for (int i = threadIdx.x; i < 8 * kExactMaxK; i += 256) {
+  const int parts = exact_parts(count, blocks_x, rows_y, k);
+  if (parts != blocks_x) {
+    // ---- few rows: one gallery pass for all of them
+    const int part = blockIdx.y * blocks_x + blockIdx.x;
+    for (int i = threadIdx.x; i < count * 512; i += 256) s_probe[i >> 9][i & 511] = p.probes[static_cast<size_t>(p.rows[i >> 9]) * 512 + (i & 511)];
+    for (int i = threadIdx.x; i < 8 * kExactFewRows * kExactFewK; i += 256) {
       (&w_sc[0][0])[i] = -INFINITY;
       (&w_ix[0][0])[i] = -1;
     }
     __syncthreads();
+    // (ncu: 149 us for 4 flagged rows x 125 k gallery rows, bound by instruction issue - 197 instructions per (gallery
+    // row, probe), half of them float -> double conversions on the XU pipe.  Variants measured and dropped,
+    // tools/bench_match.py with FRB_PROBES=random: requesting the next gallery row before scoring the current one, a grid
+    // resident in one wave, probes kept as f64 in shared memory: 163-172 us; an fp32 screen in front of the f64 dot:
+    // 201 us - with 9472 warp-private lists each seeing ~13 rows the lists never get selective)
     for (long long g = static_cast<long long>(part) * 8 + warp; g < p.N; g += static_cast<long long>(parts) * 8) {
-      const double s = warp_dot512_f64(p.gallery + g * 512, s_probe, lane);
+      float gr[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) gr[j] = p.gallery[g * 512 + lane + 32 * j];
+      for (int f = 0; f < count; ++f) {
+        double* ls = &w_sc[warp][f * kExactFewK];
+        int* li = &w_ix[warp][f * kExactFewK];
+        // exact score: same summation order as warp_dot512_f64 (the same bits on every path)
+        double sdot = 0.0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sdot = fma(static_cast<double>(gr[j]), static_cast<double>(s_probe[f][lane + 32 * j]), sdot);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+        if (lane == 0 && cand_before(sdot, g, ls[k - 1], li[k - 1])) {
+          int j = k - 1;
+          while (j > 0 && cand_before(sdot, g, ls[j - 1], li[j - 1])) {
+            ls[j] = ls[j - 1];
+            li[j] = li[j - 1];
+            --j;
+          }
+          ls[j] = sdot;
+          li[j] = static_cast<int>(g);
+        }
+      }
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < count; f += 256) {   // thread f: 8-way merge of row f's sorted warp lists
+      int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      TopkRec* dst = p.part + (static_cast<size_t>(f) * parts + part) * k;
+      for (int r = 0; r < k; ++r) {
+        int bw = -1;
+        for (int w = 0; w < 8; ++w) {
+          if (head[w] >= k) continue;
+          const int ci = w_ix[w][f * kExactFewK + head[w]];
+          if (ci < 0) continue;
+          if (bw < 0 || cand_before(w_sc[w][f * kExactFewK + head[w]], ci, w_sc[bw][f * kExactFewK + head[bw]], w_ix[bw][f * kExactFewK + head[bw]])) bw = w;
+        }
+        TopkRec rec;
+        rec.score = bw >= 0 ? w_sc[bw][f * kExactFewK + head[bw]] : -INFINITY;
+        rec.idx = bw >= 0 ? w_ix[bw][f * kExactFewK + head[bw]] : -1;
+        if (bw >= 0) ++head[bw];
+        dst[r] = rec;
+      }
+    }
+    return;
+  }
+  // ---- many rows (or k > kExactFewK): rows strided over blockIdx.y, 74 partitions each
+  const int part = blockIdx.x;
+  for (int f = blockIdx.y; f < count; f += rows_y) {
+    const int prow = p.rows[f];
+    __syncthreads();   // the previous row's merge has read the lists
+    float* probe_f = &s_probe[0][0];
+    for (int i = threadIdx.x; i < 512; i += 256) probe_f[i] = p.probes[static_cast<size_t>(prow) * 512 + i];
+    for (int i = threadIdx.x; i < 8 * kExactFewRows * kExactFewK; i += 256) {
+      (&w_sc[0][0])[i] = -INFINITY;
+      (&w_ix[0][0])[i] = -1;
+    }
+    __syncthreads();
+    double pd[16];
+    probe_lane_f64(probe_f, lane, pd);
+    for (long long g = static_cast<long long>(part) * 8 + warp; g < p.N; g += static_cast<long long>(parts) * 8) {
+      const double s = warp_dot512_f64_pre(p.gallery + g * 512, pd, lane);
       if (lane == 0 && cand_before(s, g, w_sc[warp][k - 1], w_ix[warp][k - 1])) {
         int j = k - 1;   // sorted insertion (canonical order); rare once the list has settled
         while (j > 0 && cand_before(s, g, w_sc[warp][j - 1], w_ix[warp][j - 1])) {
@@ -1372,7 +1449,7 @@ match_exact_part_kernel(const ExactFixParams p) {
           --j;
         }
         w_sc[warp][j] = s;
-        w_ix[warp][j] = g;
+        w_ix[warp][j] = static_cast<int>(g);
       }
     }
     __syncthreads();
@@ -1392,14 +1469,23 @@ match_exact_part_kernel(const ExactFixParams p) {
         dst[r] = rec;
       }
     }
-    if (count <= rows_y) break;
   }
 }
 
 // merge of a listed row's kExactBlocks partial lists: k rounds of block arg-max in canonical order (as
 // match_exact_topk_kernel), outputs for the probe row, and - sharded - the row goes to the peers
+// dynamic shared memory: the row's partial lists (f64 score + i32 local gallery row), copied once with coalesced loads -
+// the k selection rounds then run out of shared memory (reading up to 1184 x k records from L2 in every round, a few
+// dependent loads per thread at a time, made the merge of a single flagged row cost ~100 us)
+constexpr int kExactFixMaxCand = (kExactBlocks * kExactRowsY * kExactFewK > kExactBlocks * kExactMaxK) ? kExactBlocks * kExactRowsY * kExactFewK   // parts (74 x 16) x k
+                                                                                                     : kExactBlocks * kExactMaxK;
+constexpr int kExactFixSmemBytes = kExactFixMaxCand * 12;
+
 __global__ void __launch_bounds__(128)
 match_exact_fix_kernel(const ExactFixParams p, int blocks_x, int rows_y) {
+  extern __shared__ __align__(16) uint8_t fx_raw[];
+  double* c_sc = reinterpret_cast<double*>(fx_raw);
+  int* c_ix = reinterpret_cast<int*>(c_sc + kExactFixMaxCand);
   __shared__ double s_best[128];
   __shared__ long long s_besti[128];
   __shared__ double s_out[kExactMaxK];
@@ -1408,23 +1494,38 @@ match_exact_fix_kernel(const ExactFixParams p, int blocks_x, int rows_y) {
   pdl_wait();
   const int count = *p.count;
   const int t = threadIdx.x, k = p.k;
-  const int parts = exact_parts(count, blocks_x, rows_y);   // as match_exact_part_kernel laid the lists out
+  const int parts = exact_parts(count, blocks_x, rows_y, k);   // as match_exact_part_kernel laid the lists out
   for (int f = blockIdx.x; f < count; f += gridDim.x) {
     const int prow = p.rows[f];
     const TopkRec* cand = p.part + static_cast<size_t>(f) * parts * k;
     const int C = parts * k;
+    __syncthreads();
+    for (int c0 = t; c0 < C; c0 += 128 * 8) {   // eight independent 16-byte loads in flight per thread
+      TopkRec rec[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c0 + u * 128 < C) rec[u] = cand[c0 + u * 128];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c0 + u * 128 < C) {
+          c_sc[c0 + u * 128] = rec[u].score;
+          c_ix[c0 + u * 128] = static_cast<int>(rec[u].idx);
+        }
+    }
+    __syncthreads();
     double pv = INFINITY;
     long long pi = -1;
     for (int r = 0; r < k; ++r) {
       double best = -INFINITY;
       long long besti = -1;
       for (int c = t; c < C; c += 128) {
-        const TopkRec rec = cand[c];
-        if (rec.idx < 0) continue;
-        const bool after = (pi < 0) ? true : ((rec.score < pv) || (rec.score == pv && rec.idx > pi));
-        if (after && cand_before(rec.score, rec.idx, best, besti)) {
-          best = rec.score;
-          besti = rec.idx;
+        const int ci = c_ix[c];
+        if (ci < 0) continue;
+        const double cs = c_sc[c];
+        const bool after = (pi < 0) ? true : ((cs < pv) || (cs == pv && ci > pi));
+        if (after && cand_before(cs, ci, best, besti)) {
+          best = cs;
+          besti = ci;
         }
       }
       s_best[t] = best;

@@ -14,6 +14,8 @@ st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 for P in [int(a) for a in sys.argv[1:]] or [256, 1024, 4096]:
     probes = G[torch.randint(0, N, (P,), generator=g, device=dev)] + 0.03 * torch.randn((P, 512), generator=g, device=dev)
     probes[::7] = torch.randn((probes[::7].shape[0], 512), generator=g, device=dev)
+    if os.environ.get("FRB_PROBES") == "random":      # every probe an impostor (what a shard sees for probes enrolled elsewhere)
+        probes = torch.randn((P, 512), generator=g, device=dev)
     sc = torch.empty((P, 5), dtype=torch.float32, device=dev); ix = torch.empty((P, 5), dtype=torch.int64, device=dev)
     ac = torch.empty((P,), dtype=torch.uint8, device=dev)
     f = lambda: ctx.frb_match(probes.data_ptr(), P, 5, 0.35, 1, sc.data_ptr(), ix.data_ptr(), ac.data_ptr(), None, st)
