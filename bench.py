@@ -26,8 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "aligned faces/sec embedded+matched (IR-101, 1M gallery)"
-# dram__bytes_read.sum + dram__bytes_write.sum of the persistent 66-layer run at batch 256 (ncu --set full of one launch, profiles/r01d_summary.md)
-RUN_TRAFFIC = 305.98e6 + 1145.59e6
+# dram__bytes_read.sum + dram__bytes_write.sum of the persistent 66-layer run at batch 256 (ncu --set full of one launch, profiles/r02_summary.md /
+# r02a_raw_multi.csv; round 1 measured 305.98 + 1145.59 MB)
+RUN_TRAFFIC = 293.33e6 + 1198.14e6
 UNIT = "faces/s"
 
 
@@ -524,7 +525,7 @@ def run_ours(args):
     dom_tf = fl_sum / (ms_sum / 1e3) / 1e12
     section_tf = flops_face * B / (embed_ms / 1e3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that kernel from the committed `ncu --set full`
-    # capture (profiles/r01b_summary.md); null when the dominant kernel is not the one that was captured
+    # capture (profiles/r02_summary.md for the run, r01b_summary.md for the two single-layer kernels); null when the dominant kernel is not the one that was captured
     traffic = {3: 26.94e6, 6: 57.30e6, 8: RUN_TRAFFIC}.get(dom)
     roofline = dict(bound="tensor", achieved=dom_tf, peak=peaks["tf_sustained"], unit="TFLOP/s",
                     frac=dom_tf / peaks["tf_sustained"], traffic=traffic, kernel=KNAMES[dom],
