@@ -840,7 +840,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (cudaMalloc(&ctx->d_lut, sizeof(lut)) != cudaSuccess || cudaMalloc(&ctx->d_wtab, wtab.size() * 2) != cudaSuccess ||
       cudaMemcpy(ctx->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(ctx->d_wtab, wtab.data(), wtab.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMalloc(&ctx->d_gal_maxnorm, 4) != cudaSuccess ||
+      cudaMalloc(&ctx->d_gal_maxnorm, 8) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     fprintf(stderr, "frb_ctx_create: constant upload failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
@@ -1603,7 +1603,7 @@ extern "C" int frb_gallery_upload(frb_ctx* ctx, const float* g, long long N, lon
   ctx->gal_N = N;
   ctx->gal_S = 0;  // a plain template gallery: per-identity queries need frb_gallery_upload_samples
   ctx->gal_first = first_global_id;
-  CK(cudaMemset(ctx->d_gal_maxnorm, 0, 4));
+  CK(cudaMemset(ctx->d_gal_maxnorm, 0, 8));
   if (N == 0) return 0;
   CK(cudaMemcpy(ctx->d_gal, g, static_cast<size_t>(N) * 512 * 4, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
   const long long groups = (N + kGalGroup - 1) / kGalGroup;

@@ -70,16 +70,27 @@ struct MatchSmem {
   static constexpr int kTotal = kMatchKB * kABytes + kMatchBStages * kBBytes + 256 + 1024;
 };
 
+// Insert (v, idx) into the descending list; v = -inf is a no-op (every slot "keeps").  Equal scores stay in arrival
+// order (the newcomer goes below them), so the lower column wins a tie.  Written as independent selects per slot - a
+// bubble of compare-and-swaps is a dependent chain of kCand steps, and the epilogue warps (one per scheduler) are
+// latency-bound, not issue-bound (profiles/r02_summary.md: issue active 25 % while the tensor pipe waited for them).
 __device__ __forceinline__ void cand_insert(float (&ls)[kCand], int (&li)[kCand], float v, int idx) {
-  // caller guarantees v > ls[kCand-1]; strict '>' keeps the lower index on ties
-  ls[kCand - 1] = v;
-  li[kCand - 1] = idx;
+  bool keep[kCand];
 #pragma unroll
-  for (int i = kCand - 1; i > 0; --i) {
-    if (ls[i] > ls[i - 1]) {
-      const float ts = ls[i]; ls[i] = ls[i - 1]; ls[i - 1] = ts;
-      const int ti = li[i]; li[i] = li[i - 1]; li[i - 1] = ti;
-    }
+  for (int i = 0; i < kCand; ++i) keep[i] = ls[i] >= v;
+  float nl[kCand];
+  int ni[kCand];
+  nl[0] = keep[0] ? ls[0] : v;
+  ni[0] = keep[0] ? li[0] : idx;
+#pragma unroll
+  for (int i = 1; i < kCand; ++i) {
+    nl[i] = keep[i] ? ls[i] : (keep[i - 1] ? v : ls[i - 1]);
+    ni[i] = keep[i] ? li[i] : (keep[i - 1] ? idx : li[i - 1]);
+  }
+#pragma unroll
+  for (int i = 0; i < kCand; ++i) {
+    ls[i] = nl[i];
+    li[i] = ni[i];
   }
 }
 
@@ -88,7 +99,11 @@ __device__ __forceinline__ void cand_insert(float (&ls)[kCand], int (&li)[kCand]
 // order — argmax, insert, knock out, repeat — so a warp in which a single lane has a single candidate pays ~150
 // instructions, not 32 predicated insertions (~1300): with 32 independent rows per warp SOME lane has a
 // candidate in most chunks until ~10^5 scores have been seen, and that path bounded the whole match
-// (profiles/r01c: tensor pipe 37 % active at P = 4096).
+// (profiles/r01c: tensor pipe 37 % active at P = 4096).  Round 2: the four epilogue warps of a CTA run one per
+// scheduler, so this path is bound by instruction LATENCY, not issue (profiles/r02d: issue active 25 %, tensor pipe
+// 50 % on a 125 k-row shard): the running arg-max (a dependent chain of 32 compare-selects) became a tournament tree
+// and the bubble insertion independent selects - filter 0.482 -> 0.353 ms at 4096 x 125 k, 2.575 -> 2.384 ms at
+// 4096 x 1 M (1.76 PFLOP/s).
 // `floor`: admission floor shared by all slices of the probe row (see MatchParams::row_floor): scores not above it are
 // dropped without touching the list.  It never exceeds the smallest kept score of some FULL slice list, so the bound
 // match_finalize_kernel derives from the full lists (max over slices of their last entry) already covers every
@@ -97,23 +112,35 @@ __device__ __forceinline__ void cand_scan32(float (&ls)[kCand], int (&li)[kCand]
   float m = v[0];
 #pragma unroll
   for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-  const float gate = fmaxf(ls[kCand - 1], floor);
-  if (!(m > gate)) return;
+  if (!__any_sync(0xffffffffu, m > fmaxf(ls[kCand - 1], floor))) return;
+  // Slow path, warp-uniform: every round takes each lane's best remaining score (tournament over the 32 values, the
+  // lower column wins a tie), inserts it if it clears the lane's gate and knocks it out; lanes without a candidate
+  // ride along with no-op inserts.  The tournament is a tree (depth 5) instead of a running arg-max (depth 32).
 #pragma unroll 1
   while (true) {
-    float best = v[0];
-    int bj = 0;
+    float a[16];
+    int ai[16];
 #pragma unroll
-    for (int j = 1; j < 32; ++j)
-      if (v[j] > best) {  // strict: the lowest column wins a tie
-        best = v[j];
-        bj = j;
+    for (int j = 0; j < 16; ++j) {
+      const bool r = v[2 * j + 1] > v[2 * j];
+      a[j] = r ? v[2 * j + 1] : v[2 * j];
+      ai[j] = r ? 2 * j + 1 : 2 * j;
+    }
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+      for (int j = 0; j < w; ++j) {
+        const bool r = a[2 * j + 1] > a[2 * j];
+        a[j] = r ? a[2 * j + 1] : a[2 * j];
+        ai[j] = r ? ai[2 * j + 1] : ai[2 * j];
       }
-    if (!(best > fmaxf(ls[kCand - 1], floor))) break;
-    cand_insert(ls, li, best, base + bj);
+    }
+    const bool cand = a[0] > fmaxf(ls[kCand - 1], floor);
+    if (!__any_sync(0xffffffffu, cand)) break;
+    cand_insert(ls, li, cand ? a[0] : -INFINITY, base + ai[0]);
+    const int bj = cand ? ai[0] : -1;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j == bj) v[j] = -INFINITY;
+    for (int j = 0; j < 32; ++j) v[j] = (j == bj) ? -INFINITY : v[j];
   }
 }
 
@@ -498,6 +525,9 @@ match_filter2_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
     }
   } else {
     // ---- epilogue (both CTAs): one probe row per thread, running top-kCand of the slice in registers
+    // (eight epilogue warps - two per scheduler, each pair splitting a tile's columns and keeping a list each - were
+    // measured after the insertion path had been rewritten for instruction-level parallelism: filter 0.353 vs 0.359 ms
+    // at 4096 x 125 k, but twice the lists cost the finalize kernel 0.025 ms; not kept)
     const int quad = warp & 3;
     const uint32_t t_empty_leader0 = mapa_u32(smem_u32(&t_empty[0]), 0);
     int acc = 0;
