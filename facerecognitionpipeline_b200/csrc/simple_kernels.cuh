@@ -1202,8 +1202,24 @@ match_finalize_kernel(const FinalizeParams p) {
       __syncthreads();
     }
   }
-  // exact re-score of the best R survivors (R = p.rescore <= kRescore; slots beyond R stay empty)
-  const int R = p.rescore;
+  // Error bound of the filter's scores (derivation at the proof below); every thread evaluates the same expression.
+  const float qerr = sqrtf(s_e2[0] + s_e2[1] + s_e2[2] + s_e2[3]);
+  const float qbn = sqrtf(s_b2[0] + s_b2[1] + s_b2[2] + s_b2[3]);
+  const float gmax = p.max_norm[0], gerr = p.max_norm[1];
+  const float eps = (qerr * gmax + qbn * gerr + 0.000244140625f * qbn * (gmax + gerr)) * 1.0001f + 1e-6f;
+  // exact re-score of the best R survivors (R <= p.rescore <= kRescore; slots beyond R stay empty).  Not all of
+  // p.rescore need it: k candidates have an approximate score >= a_k (the k-th best), hence an exact score
+  // >= a_k - eps, so a candidate below a_k - 2 eps has an exact score below a_k - eps and is not among the k best.
+  // On random 125 k-row shards that leaves 10-15 of 40 rows to fetch - the re-score is a gather of 2 KB gallery rows
+  // and was HBM-bound at 4096 probes (335 MB per match).
+  int R = p.rescore;
+  {
+    const int kk = static_cast<int>(min(static_cast<long long>(p.k), p.N));
+    const bool have_k = kk >= 1 && s_ix[kk - 1] >= 0;          // block-uniform
+    const float cut = have_k ? s_sc[kk - 1] - 2.f * eps - 1e-6f : -INFINITY;
+    const int need = __syncthreads_count(t < R && s_ix[t] >= 0 && s_sc[t] >= cut);   // the list is sorted: a prefix
+    if (have_k) R = max(kk, need);
+  }
   for (int c = warp; c < kRescore; c += 4) {
     const int gi = c < R ? s_ix[c] : -1;
     double sc = 0.0;
@@ -1255,10 +1271,6 @@ match_finalize_kernel(const FinalizeParams p) {
       float bound = s_excl;
       if (Cp > R && s_ix[R] >= 0) bound = fmaxf(bound, s_sc[R]);
       if (bound > -INFINITY) {
-        const float qerr = sqrtf(s_e2[0] + s_e2[1] + s_e2[2] + s_e2[3]);
-        const float qbn = sqrtf(s_b2[0] + s_b2[1] + s_b2[2] + s_b2[3]);
-        const float gmax = p.max_norm[0], gerr = p.max_norm[1];
-        const float eps = (qerr * gmax + qbn * gerr + 0.000244140625f * qbn * (gmax + gerr)) * 1.0001f + 1e-6f;
         if (s_exi[kk - 1] < 0 || s_ex[kk - 1] <= static_cast<double>(bound) + eps) flag = 1;
       }
     }
