@@ -379,20 +379,39 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
       }
       const float* bias_row = s_bias + bias_case * (BLOCK_N + kBiasPad);
+      // The shortcut rows of this thread's pixel are fetched BEFORE the wait for the accumulator, so their latency
+      // (HBM or L2, ~1 us) runs under the MMAs of the tile instead of after them.  Same-box A/B in the bench: embed
+      // 5.61-5.64 -> 5.53-5.58 ms (+1.0-1.3 % faces/s); the per-launch ncu times of the residual layers did not move
+      // (they carry 1.5x the bytes of their twins and sit at the same ~3 TB/s).  Only with whole-launch ordering (every
+      // producer finished before griddepcontrol.wait returned); in dataflow mode the accumulator barrier is what
+      // orders this thread behind the producers, and the loads stay behind it.
+      constexpr int kChunksPerWarp = BLOCK_N / 64;
+      uint4 rs[kChunksPerWarp][4];
+      const bool has_res = p.residual != nullptr && valid;
+      const bool res_early = has_res && (p.progress == nullptr || p.wait_target < 0);
+      if (res_early) {
+#pragma unroll
+        for (int k = 0; k < kChunksPerWarp; ++k) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.N + (half + 2 * k) * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rs[k][j] = __ldg(rp + j);
+        }
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 64 && pair == first_pair) SLAB_TRACE(8);
       if (threadIdx.x == 64 && pair == first_pair + pair_step) SLAB_TRACE(9);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c = half; c < ((p.debug & 8) ? 0 : BLOCK_N / 32); c += 2) {
+#pragma unroll
+      for (int k = 0; k < kChunksPerWarp; ++k) {
+        const int c = half + 2 * k;
+        if (p.debug & 8) break;
         uint32_t rr[32];
         tmem_ld_32x32(taddr + c * 32, rr);
-        uint4 rs[4];
-        if (p.residual != nullptr && valid) {
+        if (has_res && !res_early) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.N + c * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rs[j] = __ldg(rp + j);
+          for (int j = 0; j < 4; ++j) rs[k][j] = __ldg(rp + j);
         }
         tmem_ld_wait();
         if (valid && !(p.debug & 4)) {
@@ -420,7 +439,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           if (p.residual != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t w[4] = {rs[j].x, rs[j].y, rs[j].z, rs[j].w};
+              const uint32_t w[4] = {rs[k][j].x, rs[k][j].y, rs[k][j].z, rs[k][j].w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 v[8 * j + 2 * t] += __uint_as_float(w[t] << 16);
