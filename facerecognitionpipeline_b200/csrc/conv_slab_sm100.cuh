@@ -361,24 +361,41 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     int stage_buf = 0;
+    // Round 2, second pass over this epilogue.  ncu source view of the 112x112 Cout = 64 layer: the MMA warp waits for a
+    // free accumulator 14x longer than for a slab, the producer sits on a full ring - the layer is bound by the
+    // per-tile latency chain of THIS code (all eight warps serve every tile), 1.17 us per tile against 0.86 us of
+    // MMAs.  19 % of the epilogue samples were the per-tile index arithmetic (two integer divisions through
+    // MUFU.RCP), 21 % waits on generic LD.E loads of the PReLU slopes from shared memory, 26 % the TMEM load together
+    // with generic loads of the bias row.  Hence: everything that depends only on the thread is computed once, the
+    // tile's position in its image is tracked incrementally (no division), the output offset is tile * R * W + t,
+    // shared-memory tables are read with ld.shared, and for BLOCK_N = 64 (one 32-column chunk per warp) the slopes
+    // live in registers for the whole kernel.
+    const int i = quad * 32 + lane;             // accumulator row = padded position in the tile
+    const int ri = i / Wp, wi = i - ri * Wp;
+    const bool valid_pos = (ri < p.R) && (wi < p.W);
+    const int t_pix = ri * p.W + wi;            // pixel of the tile (row of the staging buffer, offset in the output)
+    const int cc = (wi == 0) ? 0 : ((wi == p.W - 1) ? 2 : 1);
+    const int tile_step = 2 * pair_step;
+    const int th_step = tile_step % tiles_per_img;
+    int th = (first_pair * 2 + crank) % tiles_per_img;   // index of the tile inside its image
+    float slope[(BLOCK_N == 64) ? 32 : 1];
+    if (BLOCK_N == 64 && p.prelu != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) lds_f32x4(smem_u32(s_prelu + half * 32 + 4 * j), slope[4 * j], slope[4 * j + 1], slope[4 * j + 2], slope[4 * j + 3]);
+    }
     for (int pair = first_pair; pair < total_pairs; pair += pair_step) {
       const int tile = pair * 2 + crank;
-      const int i = quad * 32 + lane;           // accumulator row = padded position in the tile
-      const int ri = i / Wp, wi = i - ri * Wp;
-      const bool valid = (tile < num_tiles) && (ri < p.R) && (wi < p.W);
-      int bias_case = 0, img = 0;
-      size_t m = 0;
-      if (valid) {
-        img = tile / tiles_per_img;
-        const int h = (tile - img * tiles_per_img) * p.R + ri;
-        m = (static_cast<size_t>(img) * p.H + h) * p.W + wi;
-        if (p.bias_cases == 9) {
-          const int rc = (h == 0) ? 0 : ((h == p.H - 1) ? 2 : 1);
-          const int cc = (wi == 0) ? 0 : ((wi == p.W - 1) ? 2 : 1);
-          bias_case = rc * 3 + cc;
-        }
+      const bool valid = (tile < num_tiles) && valid_pos;
+      int bias_case = 0;
+      const size_t m = static_cast<size_t>(tile) * (p.R * p.W) + t_pix;   // == (img * H + h) * W + wi: tiles cover whole rows, in order
+      if (p.bias_cases == 9) {
+        const int h = th * p.R + ri;
+        const int rc = (h == 0) ? 0 : ((h == p.H - 1) ? 2 : 1);
+        bias_case = valid ? rc * 3 + cc : 0;
       }
-      const float* bias_row = s_bias + bias_case * (BLOCK_N + kBiasPad);
+      th += th_step;
+      if (th >= tiles_per_img) th -= tiles_per_img;
+      const uint32_t bias_row = smem_u32(s_bias + bias_case * (BLOCK_N + kBiasPad));
       // The shortcut rows of this thread's pixel are fetched BEFORE the wait for the accumulator, so their latency
       // (HBM or L2, ~1 us) runs under the MMAs of the tile instead of after them.  Same-box A/B in the bench: embed
       // 5.61-5.64 -> 5.53-5.58 ms (+1.0-1.3 % faces/s); the per-launch ncu times of the residual layers did not move
@@ -416,24 +433,30 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         tmem_ld_wait();
         if (valid && !(p.debug & 4)) {
           float v[32];
-          const float4* bp = reinterpret_cast<const float4*>(bias_row + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = bp[j];
+            float4 b;
+            lds_f32x4(bias_row + (c * 32 + 4 * j) * 4, b.x, b.y, b.z, b.w);
             v[4 * j] = __uint_as_float(rr[4 * j]) + b.x;
             v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + b.y;
             v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + b.z;
             v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + b.w;
           }
           if (p.prelu != nullptr) {
-            const float4* s4 = reinterpret_cast<const float4*>(s_prelu + c * 32);
+            if (BLOCK_N == 64) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 sl = s4[j];
-              v[4 * j] = v[4 * j] > 0.f ? v[4 * j] : v[4 * j] * sl.x;
-              v[4 * j + 1] = v[4 * j + 1] > 0.f ? v[4 * j + 1] : v[4 * j + 1] * sl.y;
-              v[4 * j + 2] = v[4 * j + 2] > 0.f ? v[4 * j + 2] : v[4 * j + 2] * sl.z;
-              v[4 * j + 3] = v[4 * j + 3] > 0.f ? v[4 * j + 3] : v[4 * j + 3] * sl.w;
+              for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope[(BLOCK_N == 64) ? j : 0];
+            } else {
+              const uint32_t s4 = smem_u32(s_prelu + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 sl;
+                lds_f32x4(s4 + 16 * j, sl.x, sl.y, sl.z, sl.w);
+                v[4 * j] = v[4 * j] > 0.f ? v[4 * j] : v[4 * j] * sl.x;
+                v[4 * j + 1] = v[4 * j + 1] > 0.f ? v[4 * j + 1] : v[4 * j + 1] * sl.y;
+                v[4 * j + 2] = v[4 * j + 2] > 0.f ? v[4 * j + 2] : v[4 * j + 2] * sl.z;
+                v[4 * j + 3] = v[4 * j + 3] > 0.f ? v[4 * j + 3] : v[4 * j + 3] * sl.w;
+              }
             }
           }
           if (p.residual != nullptr) {
@@ -448,7 +471,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             }
           }
           if (staged) {
-            const int t = ri * p.W + wi;                       // pixel of the tile, row of the staging buffer
+            const int t = t_pix;                               // pixel of the tile, row of the staging buffer
             const uint32_t row = smem_u32(smem_stage) + stage_buf * 16384 + t * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -486,7 +509,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
         stage_buf ^= 1;
       }
-      if (p.progress != nullptr) signal_rows(p.progress, valid, img, BLOCK_N / 64, p.sig_fence != 0);
+      if (p.progress != nullptr) signal_rows(p.progress, valid, tile / tiles_per_img, BLOCK_N / 64, p.sig_fence != 0);
       if (++acc == kAcc) {
         acc = 0;
         acc_phase ^= 1;
