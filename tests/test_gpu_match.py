@@ -334,3 +334,37 @@ def test_match_enqueues_without_synchronising_and_is_graph_capturable(ctx):
         graph.replay()
         torch.cuda.synchronize()
         _check(G, probes, k, s32.cpu().numpy(), ix.cpu().numpy(), ac.cpu().numpy(), 0.4)
+
+
+@pytest.mark.parametrize("direction", ["down", "up"])
+def test_exact_under_coherent_bf16_rounding(ctx, direction):
+    """The filter's error bound is ||q - bf16(q)|| max||g|| + ||bf16(q)|| max||g - bf16(g)|| (+ accumulation): measured
+    rounding distances instead of the element-wise worst case.  Worst case FOR that bound: every element sits just inside
+    a bf16 rounding boundary on the same side, so all 512 rounding errors of a row have the sign of the element and the
+    error of a score adds up coherently instead of averaging out.  Clusters of near-duplicate gallery rows 1e-4 apart
+    in score make the approximate ranking wrong inside the cluster; the answer must still be the exact one."""
+    rng = np.random.default_rng(11 if direction == "down" else 12)
+    N, P, k = 24000, 96, 5
+
+    def edge(x):   # move every element to the bf16 value nearest below |x|, then 0.49 ulp away from it on one side
+        b = np.ascontiguousarray(x, np.float32).view(np.uint32) & np.uint32(0xFFFF0000)
+        lo = b.view(np.float32)
+        ulp = np.abs((b + np.uint32(0x00010000)).view(np.float32) - lo)
+        return (lo + np.sign(lo) * ulp * (0.49 if direction == "down" else 0.51)).astype(np.float32)
+
+    G = _unit(rng.standard_normal((N, 512)))
+    base = rng.choice(N, 40, replace=False)
+    for b in base:                                  # 30 near-duplicates of each base row
+        dup = rng.choice(N, 30, replace=False)
+        G[dup] = G[b] + 2e-4 * rng.standard_normal((30, 512)).astype(np.float32)
+    G = edge(G)                                     # not re-normalised: the rows keep their boundary values
+    probes = edge(_unit(G[base[rng.integers(0, 40, P)]] + 0.05 * rng.standard_normal((P, 512)).astype(np.float32)))
+    sc, ix, ac = _match(ctx, G, probes, k, thr=0.4, normalize=0)       # probes used as they are: boundary values on both sides
+    eidx, esc = og.search_batch(G, probes, k, normalize=False)
+    assert np.array_equal(ix, eidx)
+    assert (np.abs(sc - esc) <= SCORE_TOL * np.maximum(1.0, np.abs(esc))).all()
+    assert np.array_equal(ac.astype(bool), esc[:, 0].astype(np.float32) >= np.float32(0.4))
+    assert ctx._lib.frb_match_last_flagged(ctx.handle) < P            # the proof still passes for most rows
+    # and through the normalising path (the device rounds bf16(q / ||q||): generic probe values, boundary gallery)
+    sc, ix, ac = _match(ctx, G, probes, k, thr=0.4, normalize=1)
+    _check(G, probes, k, sc, ix, ac, 0.4)
