@@ -16,8 +16,14 @@ ncu $F -k regex:match_finalize_kernel -s 4 -c 1 -o gpurun_out/r2p_finalize $B > 
 ncu $F -k regex:stem_tc_kernel -s 4 -c 1 -o gpurun_out/r2p_stem $B > gpurun_out/r2p_ncu_stem.log 2>&1
 ncu $F -k regex:conv_slab_sm100_kernel -s 60 -c 1 -o gpurun_out/r2p_slab112 $B > gpurun_out/r2p_ncu_slab112.log 2>&1
 ncu $F -k regex:conv_slab_sm100_kernel -s 70 -c 1 -o gpurun_out/r2p_slab28 $B > gpurun_out/r2p_ncu_slab28.log 2>&1
-ls -la gpurun_out/r2p_*.ncu-rep
 # one shard of the 8-rank sharded match (4096 probes x 125 k rows) on its own
 FRB_N=125000 python tools/bench_match.py 4096 > gpurun_out/r2p_match125k_plain.log 2>&1 && \
 FRB_N=125000 ncu $F -k regex:match_filter2_kernel -s 6 -c 1 -o gpurun_out/r2p_match125k python tools/bench_match.py 4096 > gpurun_out/r2p_ncu_match125k.log 2>&1
-ls -la gpurun_out/r2p_*.ncu-rep
+# gpurun brings back at most 64 MiB: export the pages that get read and drop the reports (9 MB each)
+for f in gpurun_out/r2p_*.ncu-rep; do
+  b=${f%.ncu-rep}
+  ncu -i $f --page raw --csv > ${b}_raw.csv 2>/dev/null
+  case $b in *slab112|*match125k) ncu -i $f --page source --csv > ${b}_source.csv 2>/dev/null;; esac
+  rm -f $f
+done
+ls -la gpurun_out/r2p_*
