@@ -25,6 +25,12 @@ reference has no tests.  This module therefore restates the *published* architec
             first unit of EVERY stage (incl. 64->64 s2), bn2 -> flatten -> fc -> features(BN1d affine);
             returns the raw feature (no L2 norm inside the model).
 
+Round 2: the arithmetic of both graphs AS RESTATED HERE is checked against an independent engine - the networks
+are written out as ONNX (tests/onnx_writer.py) and run by OpenCV's dnn module; this module agrees to ~2e-5 relative
+(tests/test_oracle_backbone.py, tests/test_onnx_import.py).  For the ArcFace path that is the reference's own
+definition of the arithmetic (an ONNX runtime executing the file).  Whether the AdaFace graph restated here IS
+upstream's net.py remains unpinned.
+
 State-dict key names follow upstream so real `adaface_ir*.ckpt` state dicts load unchanged
 (face_embedder.py:51-53 strips the `model.` prefix).  All BatchNorms use eps = 1e-5, eval mode.
 """

@@ -77,7 +77,7 @@ class _Graph:
         return out
 
 
-def write_iresnet_onnx(path, sd, units, fold_conv_bn=False, gemm=True, eps=1e-5):
+def write_iresnet_onnx(path, sd, units, fold_conv_bn=False, gemm=True, eps=1e-5, batch="N"):
     """sd: insightface iresnet state dict (torch tensors); units: e.g. [3, 4, 14, 3]."""
     g = _Graph(numeric_names=fold_conv_bn)
     f32 = lambda k: sd[k].detach().cpu().numpy().astype(np.float32)
@@ -126,7 +126,59 @@ def write_iresnet_onnx(path, sd, units, fold_conv_bn=False, gemm=True, eps=1e-5)
         x = g.node("Add", [x, g.init("fc.bias", f32("fc.bias"))])
     out = bn(x, "features")
     graph = b"".join(_ld(1, n) for n in g.nodes) + _ld(2, b"iresnet") + b"".join(_ld(5, t) for t in g.inits)
-    graph += _ld(11, _ld(1, b"input.1")) + _ld(12, _ld(1, out.encode()))
+    # ValueInfoProto { name, type { tensor_type { elem_type = FLOAT, shape { dim... } } } } as every real export carries
+    def vinfo(name, dims):
+        shape = b"".join(_ld(1, _iv(1, int(d)) if isinstance(d, int) else _ld(2, d.encode())) for d in dims)
+        return _ld(1, name.encode()) + _ld(2, _ld(1, _iv(1, 1) + _ld(2, shape)))
+    graph += _ld(11, vinfo("input.1", [batch, 3, 112, 112])) + _ld(12, vinfo(out, [batch, 512]))
+    model = _iv(1, 8) + _ld(2, b"frb200-test-writer") + _ld(8, _ld(1, b"") + _iv(2, 13)) + _ld(7, graph)
+    with open(path, "wb") as f:
+        f.write(model)
+
+
+def write_adaface_onnx(path, sd, arch, eps=1e-5, batch="N"):
+    """The AdaFace IR backbone (mk-minchul/AdaFace net.py as restated by oracle/backbone.py: `input_layer`, `body.N`
+    with BN -> conv3x3 -> BN -> PReLU -> conv3x3(stride) -> BN and a MaxPool(1, stride) or conv1x1 + BN shortcut,
+    `output_layer`) as an ONNX graph, so that an independent ONNX engine can be run against the oracle's forward.
+    Output = the 512 features BEFORE the L2 normalisation."""
+    from oracle import backbone as ob
+    g = _Graph(numeric_names=False)
+    f32 = lambda k: sd[k].detach().cpu().numpy().astype(np.float32)
+
+    def bn(x, prefix, c):
+        w = f32(prefix + ".weight") if prefix + ".weight" in sd else np.ones(c, np.float32)
+        b = f32(prefix + ".bias") if prefix + ".bias" in sd else np.zeros(c, np.float32)
+        ins = [g.init(prefix + ".weight", w), g.init(prefix + ".bias", b),
+               g.init(prefix + ".running_mean", f32(prefix + ".running_mean")), g.init(prefix + ".running_var", f32(prefix + ".running_var"))]
+        return g.node("BatchNormalization", [x] + ins, epsilon=float(eps), momentum=0.9)
+
+    def conv(x, wkey, k, stride):
+        pad = [1, 1, 1, 1] if k == 3 else [0, 0, 0, 0]
+        return g.node("Conv", [x, g.init(wkey, f32(wkey))], dilations=[1, 1], group=1, kernel_shape=[k, k], pads=pad, strides=[stride, stride])
+
+    def prelu(x, key):
+        return g.node("PRelu", [x, g.init(key, f32(key).reshape(-1, 1, 1))])
+
+    hk = ob.head_keys("adaface")
+    x = prelu(bn(conv("input.1", hk["stem_conv"], 3, 1), hk["stem_bn"], 64), hk["stem_prelu"])
+    for keys, in_c, d, s, has_sc in ob.unit_key_list(arch, "adaface"):
+        if has_sc:
+            sc = bn(conv(x, keys["sc_conv"], 1, s), keys["sc_bn"], d)
+        else:
+            sc = g.node("MaxPool", [x], kernel_shape=[1, 1], pads=[0, 0, 0, 0], strides=[s, s])
+        r = conv(bn(x, keys["bn1"], in_c), keys["conv1"], 3, 1)
+        r = prelu(bn(r, keys["bn2"], d), keys["prelu"])
+        r = bn(conv(r, keys["conv2"], 3, s), keys["bn3"], d)
+        x = g.node("Add", [r, sc])
+    x = g.node("Flatten", [bn(x, hk["out_bn"], 512)], axis=1)
+    x = g.node("Gemm", [x, g.init(hk["fc_w"], f32(hk["fc_w"])), g.init(hk["fc_b"], f32(hk["fc_b"]))], alpha=1.0, beta=1.0, transB=1)
+    out = bn(x, hk["feat_bn"], 512)
+
+    def vinfo(name, dims):
+        shape = b"".join(_ld(1, _iv(1, int(d)) if isinstance(d, int) else _ld(2, d.encode())) for d in dims)
+        return _ld(1, name.encode()) + _ld(2, _ld(1, _iv(1, 1) + _ld(2, shape)))
+    graph = b"".join(_ld(1, n) for n in g.nodes) + _ld(2, b"adaface_ir") + b"".join(_ld(5, t) for t in g.inits)
+    graph += _ld(11, vinfo("input.1", [batch, 3, 112, 112])) + _ld(12, vinfo(out, [batch, 512]))
     model = _iv(1, 8) + _ld(2, b"frb200-test-writer") + _ld(8, _ld(1, b"") + _iv(2, 13)) + _ld(7, graph)
     with open(path, "wb") as f:
         f.write(model)

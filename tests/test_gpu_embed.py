@@ -159,3 +159,24 @@ def test_chunked_prefetch_and_threads(ir50, ctx):
         t.join()
     assert np.array_equal(np.concatenate(out), whole)
     fe.max_batch = 256
+
+
+def test_device_adaface_embeddings_match_an_independent_onnx_engine(tmp_path):
+    """Device IR-50 (AdaFace layout) against OpenCV's dnn module running the same network as an ONNX graph on the host
+    (tests/onnx_writer.write_adaface_onnx) - a second, independent judge next to oracle/backbone.py.
+    Bar = north_star's: cosine >= 0.999 per face, norm within 1 %."""
+    cv2 = pytest.importorskip("cv2")
+    from tests.onnx_writer import write_adaface_onnx
+    sd = ob.random_state_dict("ir_50", "adaface", seed=3, calibrate=True)
+    path = str(tmp_path / "adaface_ir50.onnx")
+    write_adaface_onnx(path, sd, "ir_50", batch=6)
+    rng = np.random.default_rng(8)
+    crops = [cv2.resize(rng.integers(0, 256, (14, 14, 3), dtype=np.uint8), (112, 112), interpolation=cv2.INTER_CUBIC) for _ in range(6)]
+    fe = FaceEmbedder("ir_50", model_type="adaface", state_dict=sd)
+    dev = fe.extract_embeddings_batch(crops, normalize=False)      # features / ||features|| as the model returns them
+    net = cv2.dnn.readNetFromONNX(path)
+    net.setInput(np.concatenate([fe.preprocess(c) for c in crops]))
+    ref = net.forward()
+    ref_unit = ref / np.linalg.norm(ref, axis=1, keepdims=True)
+    cos = (ref_unit * dev).sum(1) / np.linalg.norm(dev, axis=1)
+    assert cos.min() >= 0.999, cos

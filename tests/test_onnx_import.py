@@ -74,3 +74,60 @@ def test_arcface_embedder_from_onnx_equals_state_dict_path(tmp_path, sd50):
     assert np.array_equal(a, b)                                           # same program bytes -> same bits
     with pytest.raises(ValueError, match="ir_50"):
         FaceEmbedder("ir_101", model_path=path, model_type="arcface")     # the file holds the other depth
+
+
+def _opencv_dnn():
+    try:
+        import cv2
+        cv2.dnn.readNetFromONNX
+        return cv2
+    except Exception:                                   # pragma: no cover - the image ships opencv with dnn
+        pytest.skip("OpenCV dnn module not available")
+
+
+@pytest.fixture(scope="module")
+def sd50_cal():
+    return ob.random_state_dict("ir_50", "iresnet", seed=5, calibrate=True)      # BN statistics calibrated: activations stay O(1)
+
+
+@pytest.mark.parametrize("fold", [False, True])
+def test_oracle_iresnet_equals_an_independent_onnx_engine(tmp_path, sd50_cal, fold):
+    """Pin for the ArcFace path.  The reference runs `arcface_ir*_ms1mv3.onnx` through an ONNX runtime
+    (face_embedder.py:64-88, insightface model_zoo), i.e. its arithmetic is "whatever the ONNX operator semantics say
+    for this graph".  OpenCV's dnn module is an independent implementation of those semantics (Conv padding / strides,
+    BatchNormalization epsilon, PRelu slope broadcasting, Gemm transB, Flatten): it must agree with oracle/backbone.py's
+    iresnet forward on the same export - kept-BN and exporter-folded flavours."""
+    cv2 = _opencv_dnn()
+    path = str(tmp_path / "arcface_ir50.onnx")
+    write_iresnet_onnx(path, sd50_cal, weights.UNITS["ir_50"], fold_conv_bn=fold, batch=2)
+    x = np.random.default_rng(0).standard_normal((2, 3, 112, 112)).astype(np.float32)
+    net = cv2.dnn.readNetFromONNX(path)
+    net.setInput(x)
+    ref = net.forward()
+    with torch.no_grad():
+        got = ob.forward(sd50_cal, torch.from_numpy(x), "ir_50", "iresnet").numpy()
+    assert ref.shape == got.shape == (2, 512)
+    assert np.abs(ref - got).max() <= 1e-4 * np.abs(ref).max()           # fp32 engines, different summation orders
+    cos = (ref * got).sum(1) / np.linalg.norm(ref, axis=1) / np.linalg.norm(got, axis=1)
+    assert cos.min() > 0.999999
+
+
+@pytest.mark.gpu
+def test_device_arcface_embeddings_match_the_independent_onnx_engine(tmp_path, sd50_cal):
+    """Same pin, one step further: crops -> FaceEmbedder(model_path=<onnx>) on the device against OpenCV dnn running
+    the file on the host, fed with FaceEmbedder.preprocess (the reference's own preprocessing, face_embedder.py:93-110).
+    Tolerance = north_star's embedding bar (cosine >= 0.999; the device computes in bf16)."""
+    cv2 = _opencv_dnn()
+    from facerecognitionpipeline_b200.face_embedder import FaceEmbedder
+    path = str(tmp_path / "arcface_ir50_ms1mv3.onnx")
+    write_iresnet_onnx(path, sd50_cal, weights.UNITS["ir_50"], batch=4)
+    rng = np.random.default_rng(4)
+    base = rng.integers(0, 256, (4, 14, 14, 3), dtype=np.uint8)
+    crops = [cv2.resize(b, (112, 112), interpolation=cv2.INTER_CUBIC) for b in base]     # smooth, face-like spectra
+    emb = FaceEmbedder("ir_50", model_path=path, model_type="arcface")
+    dev = emb.extract_embeddings_batch(crops, normalize=False)
+    net = cv2.dnn.readNetFromONNX(path)
+    net.setInput(np.concatenate([emb.preprocess(c) for c in crops]))
+    ref = net.forward()
+    cos = (ref * dev).sum(1) / np.linalg.norm(ref, axis=1) / np.linalg.norm(dev, axis=1)
+    assert cos.min() >= 0.999, cos

@@ -72,3 +72,28 @@ def test_border_bias_table_cases():
     assert tab[0, 0] == 5 + 6 + 8 + 9           # top-left corner keeps taps (1,1),(1,2),(2,1),(2,2)
     assert tab[8, 0] == 1 + 2 + 4 + 5           # bottom-right corner
     assert tab[1, 0] == 4 + 5 + 6 + 7 + 8 + 9   # top edge drops r = 0
+
+
+@pytest.mark.parametrize("arch", ["ir_50", "ir_101"])
+def test_adaface_forward_equals_an_independent_onnx_engine(tmp_path, arch):
+    """The oracle's AdaFace forward against OpenCV's dnn module running the same network written out as an ONNX graph
+    (tests/onnx_writer.write_adaface_onnx): two independent implementations of conv padding / stride placement, the
+    MaxPool(1, stride) shortcut, BatchNorm epsilon, PReLU broadcasting, NCHW flatten order and the affine-free last
+    BatchNorm.  What stays unpinned is whether this graph IS mk-minchul/AdaFace's net.py (un-vendored, no weights in
+    the reference); the arithmetic of the graph as restated is pinned to 1e-4 relative."""
+    cv2 = pytest.importorskip("cv2")
+    if not hasattr(cv2, "dnn"):
+        pytest.skip("OpenCV without dnn")
+    import numpy as np
+    from tests.onnx_writer import write_adaface_onnx
+    sd = ob.random_state_dict(arch, "adaface", seed=3, calibrate=True)
+    path = str(tmp_path / "adaface.onnx")
+    write_adaface_onnx(path, sd, arch, batch=2)
+    x = np.random.default_rng(1).standard_normal((2, 3, 112, 112)).astype(np.float32)
+    net = cv2.dnn.readNetFromONNX(path)
+    net.setInput(x)
+    ref = net.forward()
+    feat, norm = ob.forward(sd, torch.from_numpy(x), arch, "adaface")
+    got = (feat * norm).numpy()
+    assert np.abs(ref - got).max() <= 1e-4 * np.abs(ref).max()
+    assert np.allclose(np.linalg.norm(ref, axis=1), norm.flatten().numpy(), rtol=1e-5)
