@@ -23,7 +23,11 @@ namespace frb {
 constexpr int kStemRows = 8;          // image rows per CTA
 constexpr int kStemThreads = 128;
 constexpr int kStemInStride = 352;    // bf16 elements per staged input row: 8 lead (5 unused + 1 zero pixel) + 336 + 8
-constexpr int kStemSmemBytes = 16384 /*A*/ + 8192 /*B*/ + 16384 /*out*/ + (kStemRows + 2) * kStemInStride * 2 + 512 + 64 + 1024;
+// Shared memory bounds the occupancy of this kernel (a chain of dependent steps per image row, so the rows in flight
+// per SM are what hides its latencies): with a separate 16 KB output tile a CTA took 50.6 KB = 4 CTAs per SM.  The
+// output tile now reuses the A tile (the MMAs of a row have finished reading it when the epilogue runs; the next
+// row's gather waits until the TMA store has finished reading it): 34 KB = 6 CTAs per SM.
+constexpr int kStemSmemBytes = 16384 /*A, then the output tile*/ + 8192 /*B*/ + (kStemRows + 2) * kStemInStride * 2 + 512 + 64 + 1024;
 
 // w: [64][32] bf16 K-major (k = (r*3+s)*3 + c, 27..31 zero), bias/prelu: [64] fp32.
 // in: [B][H][W][3] bf16 with W == 112 (one TMEM lane per pixel of a row), out via tmOut: 2-D [B*H*W][64] bf16,
@@ -36,8 +40,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + 16384;
-  uint8_t* sOut = smem + 16384 + 8192;
-  __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(smem + 16384 + 8192 + 16384);
+  uint8_t* sOut = sA;
+  __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(smem + 16384 + 8192);
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sIn) + (kStemRows + 2) * kStemInStride * 2);
   float* s_prelu = s_bias + 64;
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_prelu + 64);
@@ -94,6 +98,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
   uint32_t phase = 0;
 
   for (int ry = 0; ry < kStemRows; ++ry) {
+    if (ry > 0) {   // the previous row's store has finished reading the tile the gather is about to overwrite
+      if (tid == 0) tma_store_wait_read<0>();
+      __syncthreads();
+    }
     // ---- gather: pixel x = tid, K index (r*3+s)*3+c = 9 contiguous staged values (18 bytes) per filter row r.
     // ncu (profiles/r02_summary.md): this kernel is bound by the shared-memory data pipe (75 % of its wavefront peak),
     // most of it the 27 two-byte GENERIC loads per pixel this gather used to issue (7.5 wavefronts each).  Now: five
@@ -130,7 +138,6 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_row + ((c ^ (tid & 7)) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
                      "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
     }
-    if (tid == 0) tma_store_wait_read<0>();  // the previous row's store has finished reading sOut
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
