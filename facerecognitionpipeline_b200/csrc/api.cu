@@ -35,6 +35,7 @@ struct Plan {  // per-batch-size launch plan of the backbone
   bool dataflow = false;
   const void* d_in = nullptr;  // the descriptors bake in the batch size and the input pointer
   std::vector<CUtensorMap> tmA, tmA2, tmB;
+  std::vector<CUtensorMap> tmR;    // slab layers with sp.res_tma: the shortcut as a TMA tile source
   std::vector<GemmParams> gp;
   std::vector<int> block_n, grid;
   size_t tail_flags = 0;           // split-K flags of all layers (zeroed at the start of every embed)
@@ -94,6 +95,7 @@ struct frb_ctx {
   int quad_clusters = 0;
   int use_slab = 1;   // activation-slab kernel for eligible 3x3 stride-1 layers (FRB_SLAB=0 disables)
   int slab_stage_out = 1;   // Cout = 64 slab layers: output staged in shared memory + one TMA store per tile (FRB_SLAB_STAGE=0: direct stores)
+  int slab_res_tma = 1;     // shortcut tile of the staged Cout = 64 layers by TMA into the staging buffer (FRB_SLAB_RES_TMA=0: per-thread loads)
   int embed_chunk = 256;  // faces per pass of the layer program (FRB_EMBED_CHUNK; 0 = whole batch in one pass)
   int use_pdl = 1;    // programmatic dependent launch between backbone kernels (FRB_PDL=0 disables)
   int match_pair = 1;   // CTA-pair match filter for P > 128 (FRB_MATCH_PAIR=0 disables)
@@ -565,7 +567,7 @@ bool slab_eligible(const frb_ctx* ctx, const frb_layer_desc& L, bool has_sc) {
 
 int setup_slab(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, const void* d_res, const void* d_w,
                const float* d_bias, const float* d_prelu, void* d_out, CUtensorMap* tmX, CUtensorMap* tmB,
-               SlabParams* sp, int* smem_bytes, int* grid, CUtensorMap* tmOut = nullptr) {
+               SlabParams* sp, int* smem_bytes, int* grid, CUtensorMap* tmOut = nullptr, CUtensorMap* tmRes = nullptr) {
   const int W = L.win, R = slab_rows(W);
   const int chunks = L.cin / 64, num_kb = 9 * chunks;
   memset(sp, 0, sizeof(*sp));
@@ -578,7 +580,9 @@ int setup_slab(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, c
   const int b_bytes = (L.cout / 2) * 128;
   // Cout = 64 layers (112 / 56 pixels): output staged in shared memory + one TMA store per tile (conv_slab_sm100.cuh)
   const bool stage_out = tmOut != nullptr && ctx->slab_stage_out && !ctx->slab_multi && L.cout == 64 && L.cin == 64 && !ctx->use_dataflow && R * W == 112;
-  const int misc = 1024 + 10 * L.cout * 4 + 9 * kBiasPad * 4 + 1024 + (stage_out ? kSlabStageBytes : 0);
+  // ... and their shortcut tile comes in by TMA into the same staging buffers (three instead of two: fetched two tiles ahead)
+  const bool res_tma = stage_out && tmRes != nullptr && d_res != nullptr && ctx->slab_res_tma;
+  const int misc = 1024 + 10 * L.cout * 4 + 9 * kBiasPad * 4 + 1024 + slab_stage_bufs(stage_out, res_tma) * kSlabStageBuf;
   const int total = 227 * 1024;
   // A unit (one 64-channel chunk of a tile's slab) is only 36 MMAs (0.6-2.4 us): several must be in flight
   // to hide the ~2 us load latency.  Weights stay resident when three units still fit beside them.
@@ -595,6 +599,7 @@ int setup_slab(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, c
   sp->b_stages = st;
   sp->nbuf = nbuf;
   sp->stage_out = stage_out ? 1 : 0;
+  sp->res_tma = res_tma ? 1 : 0;
   *smem_bytes = nbuf * sp->slab_bytes + st * b_bytes + misc;
   sp->bias = d_bias; sp->bias_cases = L.bias_cases;
   sp->prelu = L.has_prelu ? d_prelu : nullptr;
@@ -611,15 +616,22 @@ int setup_slab(frb_ctx* ctx, const frb_layer_desc& L, int B, const void* d_in, c
       *tmOut = *tmB;   // unused by the kernel
     }
   }
+  if (tmRes) {
+    if (res_tma) {
+      if (make_tmap_2d(ctx, tmRes, d_res, L.cout, static_cast<uint64_t>(B) * L.hin * W, R * W)) return 1;
+    } else {
+      *tmRes = *tmB;   // unused by the kernel
+    }
+  }
   const int pairs = (B * (L.hin / R) + 1) / 2;
   *grid = std::min(pairs, ctx->num_sms / 2) * 2;
   return 0;
 }
 
-template <int BN, int CH>
-int launch_slab_t(frb_ctx* ctx, const CUtensorMap& x, const CUtensorMap& b, const CUtensorMap& o, const SlabParams& sp, int smem_bytes,
-                  int grid, cudaStream_t st) {
-  auto kern = conv_slab_sm100_kernel<BN, CH>;
+template <int BN, int CH, bool RES = false>
+int launch_slab_t(frb_ctx* ctx, const CUtensorMap& x, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& r,
+                  const SlabParams& sp, int smem_bytes, int grid, cudaStream_t st) {
+  auto kern = conv_slab_sm100_kernel<BN, CH, RES>;
   if (set_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024)) return 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -630,19 +642,21 @@ int launch_slab_t(frb_ctx* ctx, const CUtensorMap& x, const CUtensorMap& b, cons
   fill_launch_attrs(attr, 2);
   cfg.attrs = attr;
   cfg.numAttrs = ctx->use_pdl ? 2 : 1;
-  CK(cudaLaunchKernelEx(&cfg, kern, x, b, o, sp));
+  CK(cudaLaunchKernelEx(&cfg, kern, x, b, o, r, sp));
   ctx->launches++;
   return 0;
 }
 
-int launch_slab(frb_ctx* ctx, int chunks, const CUtensorMap& x, const CUtensorMap& b, const CUtensorMap& o, const SlabParams& sp,
-                int smem_bytes, int grid, cudaStream_t st) {
+// r: tensor map of the shortcut for sp.res_tma layers (setup_slab's tmRes), any valid map otherwise
+int launch_slab(frb_ctx* ctx, int chunks, const CUtensorMap& x, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& r,
+                const SlabParams& sp, int smem_bytes, int grid, cudaStream_t st) {
   if (chunks == 1) {
-    if (sp.N == 64) return launch_slab_t<64, 1>(ctx, x, b, o, sp, smem_bytes, grid, st);
-    if (sp.N == 128) return launch_slab_t<128, 1>(ctx, x, b, o, sp, smem_bytes, grid, st);
+    if (sp.N == 64 && sp.res_tma) return launch_slab_t<64, 1, true>(ctx, x, b, o, r, sp, smem_bytes, grid, st);
+    if (sp.N == 64) return launch_slab_t<64, 1>(ctx, x, b, o, r, sp, smem_bytes, grid, st);
+    if (sp.N == 128) return launch_slab_t<128, 1>(ctx, x, b, o, r, sp, smem_bytes, grid, st);
   } else if (chunks == 2) {
-    if (sp.N == 128) return launch_slab_t<128, 2>(ctx, x, b, o, sp, smem_bytes, grid, st);
-    if (sp.N == 256) return launch_slab_t<256, 2>(ctx, x, b, o, sp, smem_bytes, grid, st);
+    if (sp.N == 128) return launch_slab_t<128, 2>(ctx, x, b, o, r, sp, smem_bytes, grid, st);
+    if (sp.N == 256) return launch_slab_t<256, 2>(ctx, x, b, o, r, sp, smem_bytes, grid, st);
   }
   return fail(ctx, "slab conv: unsupported Cin chunks %d / Cout %d", chunks, sp.N);
 }
@@ -769,6 +783,7 @@ extern "C" int frb_ctx_create(int device, frb_ctx** out) {
   if (const char* e = getenv("FRB_CONV_MODE")) ctx->conv_mode = atoi(e);
   if (const char* e = getenv("FRB_SLAB")) ctx->use_slab = atoi(e);
   if (const char* e = getenv("FRB_SLAB_STAGE")) ctx->slab_stage_out = atoi(e);
+  if (const char* e = getenv("FRB_SLAB_RES_TMA")) ctx->slab_res_tma = atoi(e);
   if (const char* e = getenv("FRB_QUAD")) ctx->conv_quad = atoi(e);
   if (const char* e = getenv("FRB_MULTI")) ctx->conv_multi = atoi(e);
   // Nsight Compute / compute-sanitizer cannot run the cooperative cluster launch of the persistent runs (the launch
@@ -1104,7 +1119,7 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
     if (units > 0x7fffffffLL) return fail(ctx, "dataflow progress counter would overflow");
   }
   pl.B = B;
-  pl.tmA.resize(nl); pl.tmA2.resize(nl); pl.tmB.resize(nl); pl.gp.resize(nl); pl.block_n.assign(nl, 0); pl.grid.assign(nl, 0);
+  pl.tmA.resize(nl); pl.tmA2.resize(nl); pl.tmB.resize(nl); pl.tmR.resize(nl); pl.gp.resize(nl); pl.block_n.assign(nl, 0); pl.grid.assign(nl, 0);
   pl.use_slab.assign(nl, 0); pl.sp.resize(nl); pl.slab_smem.assign(nl, 0);
   for (size_t i = 0; i < nl; ++i) {
     const frb_layer_desc& L = ctx->layers[i];
@@ -1121,7 +1136,7 @@ int build_plan(frb_ctx* ctx, int B, const void* d_in) {
         pl.use_slab[i] = 1;
         if (setup_slab(ctx, L, B, in, res, blob + L.w_off, reinterpret_cast<const float*>(blob + L.bias_off),
                        reinterpret_cast<const float*>(blob + L.prelu_off), ctx->d_bufs[L.out_buf], &pl.tmA[i], &pl.tmB[i],
-                       &pl.sp[i], &pl.slab_smem[i], &pl.grid[i], &pl.tmA2[i]))
+                       &pl.sp[i], &pl.slab_smem[i], &pl.grid[i], &pl.tmA2[i], &pl.tmR[i]))
           return 1;
         memset(&pl.gp[i], 0, sizeof(GemmParams));
         pl.gp[i].M = 1;  // plan marker: non-empty
@@ -1426,7 +1441,7 @@ int embed_chunk_locked(frb_ctx* ctx, const void* d_in, int Bn, int l2, int renor
       if (L.op == FRB_OP_STEM) {
         if (launch_stem(ctx, L, fp.tmA[c][i], static_cast<const uint8_t*>(d_in) + fp.c0[c] * face_bytes, fp.sub, nullptr, st)) return 1;
       } else if (fp.use_slab[i]) {
-        if (launch_slab(ctx, L.cin / 64, fp.tmA[c][i], fp.tmB[c][i], fp.tmA2[c][i], fp.sp[c][i], fp.slab_smem[i], fp.grid[i], st)) return 1;
+        if (launch_slab(ctx, L.cin / 64, fp.tmA[c][i], fp.tmB[c][i], fp.tmA2[c][i], fp.tmB[c][i], fp.sp[c][i], fp.slab_smem[i], fp.grid[i], st)) return 1;
       } else if (launch_conv(ctx, fp.block_n[i], fp.tmA[c][i], fp.tmA2[c][i], fp.tmB[c][i], fp.gp[c][i], fp.grid[i], st)) return 1;
     }
   for (size_t i = static_cast<size_t>(fp.nf); i < ctx->layers.size(); ++i) {
@@ -1454,7 +1469,7 @@ int embed_chunk_locked(frb_ctx* ctx, const void* d_in, int Bn, int l2, int renor
       if (launch_stem(ctx, L, pl.tmA[i], in, Bn, dataflow ? ctx->d_progress : static_cast<int*>(nullptr), st)) return 1;
     } else if (L.op == FRB_OP_CONV) {
       if (pl.use_slab[i]) {
-        if (launch_slab(ctx, L.cin / 64, pl.tmA[i], pl.tmB[i], pl.tmA2[i], pl.sp[i], pl.slab_smem[i], pl.grid[i], st)) return 1;
+        if (launch_slab(ctx, L.cin / 64, pl.tmA[i], pl.tmB[i], pl.tmA2[i], pl.tmR[i], pl.sp[i], pl.slab_smem[i], pl.grid[i], st)) return 1;
       } else if (launch_conv(ctx, pl.block_n[i], pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
     } else if (L.op == FRB_OP_FC) {
       if (launch_gemm(ctx, 256, A_TILED, 1, pl.tmA[i], pl.tmA2[i], pl.tmB[i], pl.gp[i], pl.grid[i], st)) return 1;
@@ -2559,8 +2574,9 @@ extern "C" int frb_debug_conv(frb_ctx* ctx, const frb_layer_desc* L, int B, cons
   if (slab_eligible(ctx, LL, d_sc != nullptr)) {
     SlabParams sp;
     int smem_bytes;
-    if (setup_slab(ctx, LL, B, d_in, d_res, d_w, d_bias, d_prelu, d_out, &a, &b, &sp, &smem_bytes, &grid, &a2)) return 1;
-    return launch_slab(ctx, LL.cin / 64, a, b, a2, sp, smem_bytes, grid, st);
+    CUtensorMap r;
+    if (setup_slab(ctx, LL, B, d_in, d_res, d_w, d_bias, d_prelu, d_out, &a, &b, &sp, &smem_bytes, &grid, &a2, &r)) return 1;
+    return launch_slab(ctx, LL.cin / 64, a, b, a2, r, sp, smem_bytes, grid, st);
   }
   if (setup_conv(ctx, LL, B, d_in, d_sc, d_res, d_w, d_bias, d_prelu, d_out, &a, &a2, &b, &gp, &bn, &grid)) return 1;
   if (gp.tail_split > 1) {

@@ -39,9 +39,12 @@ struct SlabParams {
   int wait_target;
   int sig_fence;         // experiments only: 0 drops the release fence (UNSAFE)
   int stage_out;         // 1: the epilogue stages a tile's output in shared memory and ONE TMA store writes it (tmOut)
+  int res_tma;           // 1 (only with stage_out): RES_TMA instantiation - the shortcut tile arrives by TMA (tmRes) in the
+                         // tile's staging buffer; the map describes the residual as [pixels][64 channels] like tmOut
 };
 
-constexpr int kSlabStageBytes = 2 * 16384;   // two staging buffers of 112 pixels x 64 channels (swizzled 128-byte rows)
+constexpr int kSlabStageBuf = 16384;         // one staging buffer: 112 pixels x 64 channels (swizzled 128-byte rows)
+__host__ __device__ __forceinline__ int slab_stage_bufs(int stage_out, int res_tma) { return stage_out ? (res_tma ? 3 : 2) : 0; }
 
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
                                              int c2, int c3) {
@@ -85,10 +88,13 @@ constexpr int kSlabMaxBuf = 6;
 
 // K blocks are visited chunk-major: unit (tile, cc) runs its nine taps against weight K block tap*CHUNKS+cc,
 // so a slab buffer holds ONE 64-channel chunk and is released after 36 MMAs.
-template <int BLOCK_N, int CHUNKS>
+// RES_TMA (its own instantiation, so the layers without a shortcut keep exactly the code they had): the shortcut tile
+// comes in by TMA (tmRes) into the tile's staging buffer - see the epilogue.
+template <int BLOCK_N, int CHUNKS, bool RES_TMA = false>
 __global__ void __launch_bounds__(kGemm2Threads, 1)
 conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ CUtensorMap tmOut, const SlabParams p) {
+                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                       const SlabParams p) {
   constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;
   constexpr int kAcc = (512 / BLOCK_N) < 4 ? (512 / BLOCK_N) : 4;  // TMEM accumulator stages
   constexpr int kNumKb = 9 * CHUNKS;
@@ -96,8 +102,9 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_slab = smem;                                  // [nbuf][slab_bytes]
   uint8_t* smem_b = smem + p.nbuf * p.slab_bytes;             // [b_stages][kBBytes]
-  uint8_t* smem_stage = smem_b + p.b_stages * kBBytes;        // [2][16 KB] output staging (only with p.stage_out)
-  uint8_t* tail = smem_stage + (p.stage_out ? kSlabStageBytes : 0);
+  uint8_t* smem_stage = smem_b + p.b_stages * kBBytes;        // [2 or 3][16 KB] output staging (only with p.stage_out)
+  const int n_stage = slab_stage_bufs(p.stage_out, RES_TMA ? 1 : 0);
+  uint8_t* tail = smem_stage + n_stage * kSlabStageBuf;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* slab_full = bars;                             // [6]  leader only
   uint64_t* slab_empty = bars + kSlabMaxBuf;              // [6]  per CTA
@@ -106,6 +113,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   uint64_t* tmem_full_bar = b_empty + kSlabMaxBStages;    // [4] per CTA
   uint64_t* tmem_empty_bar = tmem_full_bar + 4;           // [4] leader only, 16 arrivals
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 4);
+  uint64_t* res_full = tmem_empty_bar + 5;                // [3] per CTA: the shortcut tile has landed in staging buffer i
   float* s_bias = reinterpret_cast<float*>(tail + 1024);      // [9][BLOCK_N]
   float* s_prelu = s_bias + 9 * (BLOCK_N + kBiasPad);
 
@@ -140,6 +148,8 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
+    for (int i = 0; i < 3; ++i) mbar_init(&res_full[i], 1);
+    if (RES_TMA) prefetch_tmap(&tmRes);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -383,7 +393,26 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll
       for (int j = 0; j < 8; ++j) lds_f32x4(smem_u32(s_prelu + half * 32 + 4 * j), slope[4 * j], slope[4 * j + 1], slope[4 * j + 2], slope[4 * j + 3]);
     }
-    for (int pair = first_pair; pair < total_pairs; pair += pair_step) {
+    // Shortcut by TMA (p.res_tma, the staged Cout = 64 layers): read thread by thread, a warp's 64-byte pieces of
+    // 32 different pixels touched 32 lines per load instruction - the same pattern the direct stores had, and the
+    // reason a conv2 (shortcut) layer took 101 us where its conv1 twin took 59.  Now the tile's 112 x 64 shortcut
+    // block is fetched into the tile's own staging buffer two tiles ahead (three buffers), every thread adds its
+    // pieces in place (same swizzled address for the read and the write) and the buffer goes out as before.
+    constexpr bool res_tma = RES_TMA;       // host side: only together with stage_out
+    auto issue_res = [&](int it_) {   // epi_tid 0 only; `it_` = index of the tile in this CTA's sequence
+      const int tl = (first_pair + it_ * pair_step) * 2 + crank;
+      if (first_pair + it_ * pair_step < total_pairs && tl < num_tiles) {
+        const int b = it_ % 3;
+        mbar_arrive_expect_tx(&res_full[b], 112 * 128);
+        tma_load_2d(&tmRes, &res_full[b], smem_stage + b * kSlabStageBuf, 0, tl * (p.R * p.W));
+      }
+    };
+    if (res_tma && epi_tid == 0) {
+      issue_res(0);
+      issue_res(1);
+    }
+    int it = 0;
+    for (int pair = first_pair; pair < total_pairs; pair += pair_step, it += res_tma ? 1 : 0) {
       const int tile = pair * 2 + crank;
       const bool valid = (tile < num_tiles) && valid_pos;
       int bias_case = 0;
@@ -404,7 +433,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       // orders this thread behind the producers, and the loads stay behind it.
       constexpr int kChunksPerWarp = BLOCK_N / 64;
       uint4 rs[kChunksPerWarp][4];
-      const bool has_res = p.residual != nullptr && valid;
+      const bool has_res = p.residual != nullptr && valid && !res_tma;
       const bool res_early = has_res && (p.progress == nullptr || p.wait_target < 0);
       if (res_early) {
 #pragma unroll
@@ -416,6 +445,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
+      if (res_tma && tile < num_tiles) mbar_wait(&res_full[stage_buf], static_cast<uint32_t>((it / 3) & 1));
       if (threadIdx.x == 64 && pair == first_pair) SLAB_TRACE(8);
       if (threadIdx.x == 64 && pair == first_pair + pair_step) SLAB_TRACE(9);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
@@ -459,6 +489,13 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
               }
             }
           }
+          if (res_tma) {
+            const uint32_t rrow = smem_u32(smem_stage) + stage_buf * kSlabStageBuf + t_pix * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rs[k][j].x), "=r"(rs[k][j].y), "=r"(rs[k][j].z), "=r"(rs[k][j].w)
+                           : "r"(rrow + (((c * 4 + j) ^ (t_pix & 7)) << 4)));
+          }
           if (p.residual != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -472,7 +509,7 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           }
           if (staged) {
             const int t = t_pix;                               // pixel of the tile, row of the staging buffer
-            const uint32_t row = smem_u32(smem_stage) + stage_buf * 16384 + t * 128;
+            const uint32_t row = smem_u32(smem_stage) + stage_buf * kSlabStageBuf + t * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t ox = pack_bf16x2(v[8 * j], v[8 * j + 1]), oy = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
@@ -504,10 +541,16 @@ conv_slab_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         fence_proxy_async();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (epi_tid == 0 && tile < num_tiles) {
-          tma_store_2d(&tmOut, smem_stage + stage_buf * 16384, 0, tile * (p.R * p.W));
+          tma_store_2d(&tmOut, smem_stage + stage_buf * kSlabStageBuf, 0, tile * (p.R * p.W));
           tma_store_commit();
         }
-        stage_buf ^= 1;
+        // the buffer of tile it + 2 is the one tile it - 1 was stored from: that store has finished reading (wait above)
+        if (res_tma) {
+          if (epi_tid == 0) issue_res(it + 2);
+          stage_buf = (stage_buf == 2) ? 0 : stage_buf + 1;
+        } else {
+          stage_buf ^= 1;
+        }
       }
       if (p.progress != nullptr) signal_rows(p.progress, valid, tile / tiles_per_img, BLOCK_N / 64, p.sig_fence != 0);
       if (++acc == kAcc) {
