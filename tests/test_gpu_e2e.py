@@ -139,7 +139,8 @@ def test_launch_schedules_are_bit_identical(tmp_path):
     never what it computes.  Round 2 adds: the front (stem + 112/56-pixel layers) in sub-batches of 32 images (default),
     without them (FRB_FRONT_SUB=0), with a right-aligned overlapping last sub-batch (150 faces in 4 x 38), the pass cut
     into chunks of 64 faces (FRB_EMBED_CHUNK), the persistent slab run with the streamed weight swap, and the Cout = 64
-    slab layers with direct global stores instead of the staged TMA store (FRB_SLAB_STAGE=0)."""
+    slab layers with direct global stores instead of the staged TMA store (FRB_SLAB_STAGE=0), and their shortcut read
+    thread by thread instead of as a TMA tile (FRB_SLAB_RES_TMA=0)."""
     import os
     import subprocess
     import sys
@@ -159,7 +160,8 @@ def test_launch_schedules_are_bit_identical(tmp_path):
                       ("run_barrier", {"FRB_MULTI": "1"}), ("run_flow_plain", {"FRB_MULTI": "2", "FRB_PDL": "0"}),
                       ("dataflow", {"FRB_DATAFLOW": "1"}), ("no_front", {"FRB_FRONT_SUB": "0"}),
                       ("front_overlap", {"FRB_FRONT_SUB": "40"}), ("chunk_64", {"FRB_EMBED_CHUNK": "64"}),
-                      ("slab_run", {"FRB_SLAB_MULTI": "1"}), ("direct_stores", {"FRB_SLAB_STAGE": "0"})):
+                      ("slab_run", {"FRB_SLAB_MULTI": "1"}), ("direct_stores", {"FRB_SLAB_STAGE": "0"}),
+                      ("thread_shortcut", {"FRB_SLAB_RES_TMA": "0"})):
         out = tmp_path / f"{name}.npy"
         subprocess.run([sys.executable, str(script), str(out)], check=True, env={**os.environ, **env}, timeout=600)
         outs.append(np.load(out))
