@@ -6,15 +6,17 @@
 // image rows; per row, thread x packs pixel x's 27 inputs (+5 zeros) into a 64-byte K-major row of a
 // 128B-swizzled shared-memory tile, one elected thread issues two 128x64x16 tcgen05.mma, and the same
 // threads run the epilogue (TMEM -> +bias -> PReLU -> bf16 -> swizzled smem tile -> one TMA store of
-// the whole 112-pixel x 64-channel row, 14 KB contiguous in NHWC).  The kernel is HBM-write bound
-// (128 B out per 6 B in); several small CTAs per SM overlap gather, MMA and store by occupancy.
+// the whole 112-pixel x 64-channel row, 14 KB contiguous in NHWC).  128 B go out per 6 B that come in, but the kernel
+// is NOT bound by that write stream (3.3 TB/s where a write-only stream reaches 6.2 on this part, tools/hbm_rw_peaks.py):
+// it is a chain of dependent steps per image row (gather - barrier - MMA - wait - epilogue - barrier - store), so what
+// bounds it is how many rows an SM has in flight and how many shared-memory wavefronts each costs.
 //
-// Round 2 tried two restructurings, both bit-identical and neither faster under ncu (profiles/r02_summary.md), which
-// is what a kernel bound by the WRITE stream (not by its instruction chain) looks like: (1) two image rows per MMA step
-// (block-diagonal [128][64] weights, N = 128, 3 CTAs per SM): 175 us against 155 us; (2) two threads per pixel (256
-// threads, K halves in the gather, channel halves in the epilogue): 153 us on a box where every other kernel ran 8 %
-// faster than in round 1.  The kernel writes 411 MB per batch of 256 at 2.65 TB/s; a plain device memset on the same
-// part is the yardstick for a write-only stream (tools/hbm_rw_peaks.py), not the read+write copy figure.
+// Round 2 history (all bit-identical; profiles/r02_summary.md): two restructurings that did NOT help - two image rows
+// per MMA step (block-diagonal [128][64] weights, N = 128, 3 CTAs per SM): 175 us against 155 us; two threads per pixel
+// (256 threads, K halves in the gather, channel halves in the epilogue): 153 us.  What did: the gather's 27 two-byte
+// GENERIC loads per pixel and the epilogue's generic loads of bias / slopes replaced by aligned ld.shared (75 % -> 62 %
+// of the shared-memory wavefront peak, 155 -> 118 us), and the output tile reusing the A tile (50.6 -> 34 KB of shared
+// memory, 4 -> 6 CTAs per SM, 118 -> 105 us).
 #pragma once
 #include "ptx.cuh"
 
