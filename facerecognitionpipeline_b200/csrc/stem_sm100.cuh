@@ -28,8 +28,11 @@ constexpr int kStemInStride = 352;    // bf16 elements per staged input row: 8 l
 // Shared memory bounds the occupancy of this kernel (a chain of dependent steps per image row, so the rows in flight
 // per SM are what hides its latencies): with a separate 16 KB output tile a CTA took 50.6 KB = 4 CTAs per SM.  The
 // output tile now reuses the A tile (the MMAs of a row have finished reading it when the epilogue runs; the next
-// row's gather waits until the TMA store has finished reading it): 34 KB = 6 CTAs per SM.
-constexpr int kStemSmemBytes = 16384 /*A, then the output tile*/ + 8192 /*B*/ + (kStemRows + 2) * kStemInStride * 2 + 512 + 64 + 1024;
+// row's gather waits until the TMA store has finished reading it): 34 KB = 6 CTAs per SM.  Without a kilobyte of
+// alignment slack it is 32 192 B + 1 KB reserved = 7 CTAs per SM (7 x 64 TMEM columns and 7 x 128 x 64 registers fit as
+// well): the dynamic window of a kernel without static shared memory starts 1024-aligned (CTA allocations are
+// 1 KB-granular with 1 KB reserved in front); the kernel checks that and traps otherwise.
+constexpr int kStemSmemBytes = 16384 /*A, then the output tile*/ + 8192 /*B*/ + (kStemRows + 2) * kStemInStride * 2 + 512 + 64;
 
 // w: [64][32] bf16 K-major (k = (r*3+s)*3 + c, 27..31 zero), bias/prelu: [64] fp32.
 // in: [B][H][W][3] bf16 with W == 112 (one TMEM lane per pixel of a row), out via tmOut: 2-D [B*H*W][64] bf16,
@@ -39,7 +42,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const __nv_bfloat16* _
                const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
                const float* __restrict__ prelu, int H, int W, int* __restrict__ progress) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();   // the 128-byte swizzle of the A / B / output tiles needs it
   uint8_t* sA = smem;
   uint8_t* sB = smem + 16384;
   uint8_t* sOut = sA;
