@@ -16,7 +16,7 @@
 // (256 threads, K halves in the gather, channel halves in the epilogue): 153 us.  What did: the gather's 27 two-byte
 // GENERIC loads per pixel and the epilogue's generic loads of bias / slopes replaced by aligned ld.shared (75 % -> 62 %
 // of the shared-memory wavefront peak, 155 -> 118 us), and the output tile reusing the A tile (50.6 -> 34 KB of shared
-// memory, 4 -> 6 CTAs per SM, 118 -> 105 us).
+// memory, 4 -> 6 CTAs per SM, 118 -> 105 us; without the alignment slack 7 CTAs per SM, 100 us).
 #pragma once
 #include "ptx.cuh"
 
