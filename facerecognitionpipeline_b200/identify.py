@@ -18,7 +18,7 @@ Gallery samples must be unit-norm to within 1e-3 (ValueError otherwise): the per
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 

@@ -18,7 +18,7 @@ Anything else (a preprocessing prologue, another backbone) raises ValueError nam
 from __future__ import annotations
 
 import struct
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 

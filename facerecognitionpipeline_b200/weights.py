@@ -22,7 +22,6 @@ import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List
 
-import numpy as np
 import torch
 
 from . import _native

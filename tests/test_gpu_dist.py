@@ -7,7 +7,6 @@
   * >= 2 GPUs (skipped otherwise): one process per GPU, NCCL process group: the peer-memory exchange (cudaIpc) and the
     NCCL exchange (one packed all-gather) must both equal the unsharded match.
 """
-import ctypes as C
 import os
 import socket
 

@@ -1,5 +1,4 @@
 """Warp + normalise and preprocess kernels: byte-exact against cv2 / the reference arithmetic."""
-import ctypes as C
 
 import cv2
 import numpy as np
